@@ -1,0 +1,61 @@
+"""In-tree build of libdagr_b200.so (hand-written sm_100a kernels behind a C-ABI, no torch headers).
+
+    python -m dagr_b200.build          # nvcc -gencode arch=compute_100a,code=sm_100a -> dagr_b200/libdagr_b200.so
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libdagr_b200.so"
+SOURCES = ["capi.cu", "graph.cu", "conv_l1.cu", "coarse.cu", "masked.cu"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dagr_b200.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    nvcc = _nvcc()
+    bdir = PKG / "build"
+    bdir.mkdir(exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = bdir / (s.replace(".cu", ".o"))
+        cmd = [nvcc, "-c", str(CSRC / s), "-o", str(o)] + NVCC_FLAGS
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(o))
+    log = []
+    for s, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {s}\n{out}")
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
+    (bdir / "ptxas.log").write_text("\n".join(log))
+    cmd = [nvcc, "-shared", "-o", str(LIB)] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    subprocess.check_call(cmd)
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,581 @@
+// coarse.cu -- everything after the event level: voxel-grid pooling, SplineConv on voxel grids,
+// dense projection, decode and NMS.  sm_100a.
+//
+// After pool1 the graph has at most B*56*40 nodes and, because the event radius (r px) is smaller
+// than a pool1 voxel, every coarse edge joins 8-neighbouring voxels.  The coarse levels are therefore
+// stored as DENSE voxel grids [B, ny, nx] (valid flag, rounded pixel position, features, 8-bit
+// in-edge mask) instead of the reference's compacted node/edge lists (pooling.py:51-97).  The
+// reference's consecutive node ids / sorted unique edge lists are recovered from the grids on demand
+// (dagr_b200/export.py) for parity checks.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// pool1 finalize: one warp per voxel
+// ------------------------------------------------------------------------------------------------
+// torch.div(a, b, rounding_mode='floor') for fp32 (c10::div_floor_floating), needed because
+// floorf(a/b) differs when the rounded quotient lands on an integer from below.
+__device__ __forceinline__ float div_floor_f32(float a, float b)
+{
+    const float mod = fmodf(a, b);
+    float div = __fdiv_rn(__fsub_rn(a, mod), b);
+    if ((mod != 0.f) && ((b < 0.f) != (mod < 0.f))) div -= 1.f;
+    float fl;
+    if (div != 0.f) {
+        fl = floorf(div);
+        if (div - fl > 0.5f) fl += 1.f;
+    } else {
+        fl = copysignf(0.f, __fdiv_rn(a, b));
+    }
+    return fl;
+}
+
+__device__ __forceinline__ int round_to_pixel(float mean, int size)
+{
+    // floor((pos + 1e-5) / (1/size))   (pooling.py:47-49), wh_inv = fl(1/size)
+    const float inv = __frcp_rn((float)size);
+    const float q = div_floor_f32(__fadd_rn(mean, 1e-5f), inv);
+    const int k = (int)q;
+    return min(max(k, 0), size - 1);
+}
+
+__global__ void __launch_bounds__(128)
+k_pool1_finalize(const dagr_geom_t g, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
+                 const int2 *__restrict__ ti, const uint32_t *__restrict__ poolmax, int C,
+                 int32_t *__restrict__ cnt, int32_t *__restrict__ pxy, float *__restrict__ tmean,
+                 float *__restrict__ tmax, float *__restrict__ x)
+{
+    const int cells = g.B * g.ny1 * g.nx1;
+    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= cells) return;
+    const int s = start[(int64_t)cell * g.CP], e = start[(int64_t)(cell + 1) * g.CP];
+    long long sx = 0, sy = 0, st = 0;
+    int tm = -2147483647;
+    for (int p = s + lane; p < e; p += 32) {
+        const uint32_t w = xyb[p];
+        sx += w & 0xfff; sy += (w >> 12) & 0xfff;
+        const int t = ti[p].x;
+        st += t; tm = max(tm, t);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, d);
+        sy += __shfl_xor_sync(0xffffffffu, sy, d);
+        st += __shfl_xor_sync(0xffffffffu, st, d);
+        tm = max(tm, __shfl_xor_sync(0xffffffffu, tm, d));
+    }
+    const int n = e - s;
+    if (lane == 0) {
+        cnt[cell] = n;
+        if (n > 0) {
+            const float mx = (float)((double)sx / ((double)n * (double)g.W));
+            const float my = (float)((double)sy / ((double)n * (double)g.H));
+            pxy[2 * cell] = round_to_pixel(mx, g.W);
+            pxy[2 * cell + 1] = round_to_pixel(my, g.H);
+            tmean[cell] = (float)((double)st / ((double)n * (double)g.T));
+            tmax[cell] = __fdiv_rn((float)tm, (float)g.T);
+        } else {
+            pxy[2 * cell] = 0; pxy[2 * cell + 1] = 0; tmean[cell] = 0.f; tmax[cell] = 0.f;
+        }
+    }
+    for (int c = lane; c < C; c += 32)
+        x[(int64_t)cell * C + c] = n > 0 ? dec_ordered(poolmax[(int64_t)cell * C + c]) : 0.f;
+}
+
+extern "C" int dagr_pool1_finalize(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
+                                   const int32_t *ti, const uint32_t *poolmax, int C, int32_t *cnt, int32_t *pxy,
+                                   float *tmean, float *tmax, float *x, void *stream)
+{
+    (void)N;
+    const int cells = g->B * g->ny1 * g->nx1;
+    k_pool1_finalize<<<dagr_div_up(cells, 4), 128, 0, (cudaStream_t)stream>>>(*g, start, xyb, (const int2 *)ti, poolmax, C,
+                                                                            cnt, pxy, tmean, tmax, x);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cat(x, pos[:, :2])
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cat_pos(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t *__restrict__ pxy,
+                          const float *__restrict__ x, int Cx, float *__restrict__ xin, int64_t total)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int Ci = Cx + 2;
+    const int64_t cell = i / Ci;
+    const int c = (int)(i % Ci);
+    float v = 0.f;
+    if (cnt[cell] > 0) {
+        if (c < Cx) v = x[cell * Cx + c];
+        else if (c == Cx) v = gr.posxr[pxy[2 * cell]];
+        else v = gr.posyr[pxy[2 * cell + 1]];
+    }
+    xin[i] = v;
+}
+
+extern "C" int dagr_grid_cat_pos(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const float *x, int Cx,
+                                 float *xin, void *stream)
+{
+    const int64_t total = (int64_t)gr->B * gr->ny * gr->nx * (Cx + 2);
+    k_cat_pos<<<dagr_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(*gr, cnt, pxy, x, Cx, xin, total);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SplineConv on a voxel grid: one warp per destination voxel (v1: direct slot form)
+// ------------------------------------------------------------------------------------------------
+#define GC_WARPS 4
+#define GC_SLOTS 25
+
+__global__ void __launch_bounds__(GC_WARPS * 32)
+k_grid_conv(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t *__restrict__ pxy,
+            const uint32_t *__restrict__ mask, const float *__restrict__ xin, int Cin, int Cout,
+            const float *__restrict__ weight, const float *__restrict__ rootT, const float *__restrict__ bias,
+            const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ skip,
+            int relu, float den_x, float den_y, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float smem_f[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *A = smem_f + (size_t)warp * GC_SLOTS * Cin;          // [25][Cin]
+    const int cells = gr.B * gr.ny * gr.nx;
+    const int cell = blockIdx.x * GC_WARPS + warp;
+    if (cell >= cells) return;
+    if (cnt[cell] <= 0) {
+        for (int o = lane; o < Cout; o += 32) out[(int64_t)cell * Cout + o] = 0.f;
+        return;
+    }
+    const int per = gr.ny * gr.nx;
+    const int b = cell / per, rem = cell % per, cy = rem / gr.nx, cx = rem % gr.nx;
+    const int px = pxy[2 * cell], py = pxy[2 * cell + 1];
+    const uint32_t m = mask[cell];
+    uint32_t used = 0;
+
+    for (int i = lane; i < GC_SLOTS * Cin; i += 32) A[i] = 0.f;
+    __syncwarp();
+    for (int bit = 0; bit < 9; bit++) {
+        if (!((m >> bit) & 1u) || bit == 4) continue;
+        const int dcx = bit % 3 - 1, dcy = bit / 3 - 1;
+        const int sx = cx + dcx, sy = cy + dcy;
+        if (sx < 0 || sy < 0 || sx >= gr.nx || sy >= gr.ny) continue;
+        const int src = b * per + sy * gr.nx + sx;
+        if (cnt[src] <= 0) continue;
+        const int dx = pxy[2 * src] - px, dy = pxy[2 * src + 1] - py;
+        // attr = d / (2*M*size) + 0.5 exactly as init_lut evaluates it (spline_conv.py:28-29)
+        const float ax = __fadd_rn(__fdiv_rn((float)dx, den_x), 0.5f);
+        const float ay = __fadd_rn(__fdiv_rn((float)dy, den_y), 0.5f);
+        float w[4]; int slot[4];
+        spline_basis2(ax, ay, 5, w, slot);
+        const float *xs = xin + (int64_t)src * Cin;
+        for (int ci = lane; ci < Cin; ci += 32) {
+            const float v = xs[ci];
+#pragma unroll
+            for (int s = 0; s < 4; s++) A[slot[s] * Cin + ci] = fmaf(w[s], v, A[slot[s] * Cin + ci]);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) if (w[s] != 0.f) used |= 1u << slot[s];
+    }
+    __syncwarp();
+    const float *xd = xin + (int64_t)cell * Cin;
+    for (int o = lane; o < Cout; o += 32) {
+        float acc = 0.f;
+        uint32_t u = used;
+        while (u) {
+            const int k = __ffs(u) - 1; u &= u - 1;
+            const float *wk = weight + (int64_t)k * Cin * Cout + o;
+            const float *ak = A + k * Cin;
+            for (int ci = 0; ci < Cin; ci++) acc = fmaf(ak[ci], __ldg(wk + (int64_t)ci * Cout), acc);
+        }
+        for (int ci = 0; ci < Cin; ci++) acc = fmaf(xd[ci], __ldg(rootT + (int64_t)ci * Cout + o), acc);
+        if (bias) acc += bias[o];
+        if (scale) acc = fmaf(acc, scale[o], shift[o]);
+        if (skip) acc += skip[(int64_t)cell * Cout + o];
+        if (relu) acc = fmaxf(acc, 0.f);
+        out[(int64_t)cell * Cout + o] = acc;
+    }
+}
+
+extern "C" int dagr_grid_conv(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const uint32_t *mask,
+                              const float *xin, int Cin, int Cout, const float *weight, const float *rootT,
+                              const float *bias, const float *scale, const float *shift, const float *skip, int relu,
+                              float den_x, float den_y, float *out, void *stream)
+{
+    DAGR_CHECK_ARG(gr && Cin > 0 && Cout > 0, "bad channels");
+    const int cells = gr->B * gr->ny * gr->nx;
+    const size_t smem = (size_t)GC_WARPS * GC_SLOTS * Cin * sizeof(float);
+    DAGR_CHECK_ARG(smem <= 200 * 1024, "Cin too large for the grid conv kernel");
+    DAGR_CUDA(cudaFuncSetAttribute(k_grid_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_grid_conv<<<dagr_div_up(cells, GC_WARPS), GC_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        *gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Linear (no bias) + eval BN on valid voxels: the skip branch of ConvBlockWithSkip
+// ------------------------------------------------------------------------------------------------
+__global__ void k_grid_linear_bn(int64_t cells, const int32_t *__restrict__ cnt, const float *__restrict__ xin, int Cin,
+                                 int Cout, const float *__restrict__ wT, const float *__restrict__ scale,
+                                 const float *__restrict__ shift, float *__restrict__ out)
+{
+    const int64_t cell = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= cells) return;
+    const bool valid = cnt[cell] > 0;
+    const float *xd = xin + cell * Cin;
+    for (int o = lane; o < Cout; o += 32) {
+        float acc = 0.f;
+        if (valid) {
+            for (int ci = 0; ci < Cin; ci++) acc = fmaf(xd[ci], __ldg(wT + (int64_t)ci * Cout + o), acc);
+            if (scale) acc = fmaf(acc, scale[o], shift[o]);
+        }
+        out[cell * Cout + o] = acc;
+    }
+}
+
+extern "C" int dagr_grid_linear_bn(int64_t cells, const int32_t *cnt, const float *xin, int Cin, int Cout,
+                                   const float *wT, const float *scale, const float *shift, float *out, void *stream)
+{
+    k_grid_linear_bn<<<dagr_div_up(cells, 4), 128, 0, (cudaStream_t)stream>>>(cells, cnt, xin, Cin, Cout, wT, scale, shift, out);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling between voxel grids (pool2..4)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_grid_pool(const dagr_grid_t ch, const dagr_grid_t pa, const int32_t *__restrict__ cellx,
+                            const int32_t *__restrict__ celly, const int32_t *__restrict__ cnt,
+                            const int32_t *__restrict__ pxy, const float *__restrict__ tmean,
+                            const float *__restrict__ tmax, const uint32_t *__restrict__ mask,
+                            const float *__restrict__ x, int C, int aggr, uint32_t *__restrict__ accmax,
+                            double *__restrict__ accsum, double *__restrict__ possum, uint32_t *__restrict__ ptmax,
+                            int32_t *__restrict__ pcnt, uint32_t *__restrict__ pmask, int32_t *__restrict__ err)
+{
+    const int cells = ch.B * ch.ny * ch.nx;
+    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= cells || cnt[cell] <= 0) return;
+    const int per = ch.ny * ch.nx;
+    const int b = cell / per, rem = cell % per, cy = rem / ch.nx, cx = rem % ch.nx;
+    const int pper = pa.ny * pa.nx;
+    const int px = pxy[2 * cell], py = pxy[2 * cell + 1];
+    const int Px = cellx[px], Py = celly[py];
+    const int P = b * pper + Py * pa.nx + Px;
+    if (lane == 0) {
+        atomicAdd(pcnt + P, 1);
+        atomicAdd(possum + 3 * (int64_t)P + 0, (double)ch.posxr[px]);
+        atomicAdd(possum + 3 * (int64_t)P + 1, (double)ch.posyr[py]);
+        atomicAdd(possum + 3 * (int64_t)P + 2, (double)tmean[cell]);
+        atomicMax(ptmax + P, enc_ordered(tmax[cell]));
+        const uint32_t m = mask[cell];
+        uint32_t bits = 0;
+        for (int bit = 0; bit < 9; bit++) {
+            if (!((m >> bit) & 1u) || bit == 4) continue;
+            const int sx = cx + bit % 3 - 1, sy = cy + bit / 3 - 1;
+            if (sx < 0 || sy < 0 || sx >= ch.nx || sy >= ch.ny) continue;
+            const int src = b * per + sy * ch.nx + sx;
+            if (cnt[src] <= 0) continue;
+            const int SPx = cellx[pxy[2 * src]], SPy = celly[pxy[2 * src + 1]];
+            const int ddx = SPx - Px, ddy = SPy - Py;
+            if (ddx == 0 && ddy == 0) continue;                        // self loop dropped (pooling.py:62)
+            if (ddx < -1 || ddx > 1 || ddy < -1 || ddy > 1) { atomicExch(err, 1); continue; }
+            bits |= 1u << ((ddy + 1) * 3 + (ddx + 1));
+        }
+        if (bits) atomicOr(pmask + P, bits);
+    }
+    for (int c = lane; c < C; c += 32) {
+        const float v = x[(int64_t)cell * C + c];
+        if (aggr == 0) atomicMax(accmax + (int64_t)P * C + c, enc_ordered(v));
+        else atomicAdd(accsum + (int64_t)P * C + c, (double)v);
+    }
+}
+
+extern "C" int dagr_grid_pool(const dagr_grid_t *child, const dagr_grid_t *parent, const int32_t *cellx,
+                              const int32_t *celly, const int32_t *cnt, const int32_t *pxy, const float *tmean,
+                              const float *tmax, const uint32_t *mask, const float *x, int C, int aggr,
+                              uint32_t *accmax, double *accsum, double *possum, uint32_t *ptmax, int32_t *pcnt,
+                              uint32_t *pmask, int32_t *err_flag, void *stream)
+{
+    const int cells = child->B * child->ny * child->nx;
+    k_grid_pool<<<dagr_div_up(cells, 4), 128, 0, (cudaStream_t)stream>>>(*child, *parent, cellx, celly, cnt, pxy, tmean, tmax,
+                                                                       mask, x, C, aggr, accmax, accsum, possum, ptmax,
+                                                                       pcnt, pmask, err_flag);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+__global__ void k_grid_pool_finalize(const dagr_grid_t pa, int C, int aggr, const uint32_t *__restrict__ accmax,
+                                     const double *__restrict__ accsum, const double *__restrict__ possum,
+                                     const uint32_t *__restrict__ ptmax, const int32_t *__restrict__ pcnt,
+                                     int32_t *__restrict__ pxy, float *__restrict__ tmean, float *__restrict__ tmax,
+                                     float *__restrict__ x)
+{
+    const int cells = pa.B * pa.ny * pa.nx;
+    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= cells) return;
+    const int n = pcnt[cell];
+    if (lane == 0) {
+        if (n > 0) {
+            const float mx = (float)(possum[3 * (int64_t)cell] / (double)n);
+            const float my = (float)(possum[3 * (int64_t)cell + 1] / (double)n);
+            pxy[2 * cell] = round_to_pixel(mx, pa.W);
+            pxy[2 * cell + 1] = round_to_pixel(my, pa.H);
+            tmean[cell] = (float)(possum[3 * (int64_t)cell + 2] / (double)n);
+            tmax[cell] = dec_ordered(ptmax[cell]);
+        } else {
+            pxy[2 * cell] = 0; pxy[2 * cell + 1] = 0; tmean[cell] = 0.f; tmax[cell] = 0.f;
+        }
+    }
+    for (int c = lane; c < C; c += 32) {
+        float v = 0.f;
+        if (n > 0) v = aggr == 0 ? dec_ordered(accmax[(int64_t)cell * C + c])
+                                 : (float)(accsum[(int64_t)cell * C + c] / (double)n);
+        x[(int64_t)cell * C + c] = v;
+    }
+}
+
+extern "C" int dagr_grid_pool_finalize(const dagr_grid_t *parent, int C, int aggr, const uint32_t *accmax,
+                                       const double *accsum, const double *possum, const uint32_t *ptmax,
+                                       const int32_t *pcnt, int32_t *pxy, float *tmean, float *tmax, float *x,
+                                       void *stream)
+{
+    const int cells = parent->B * parent->ny * parent->nx;
+    k_grid_pool_finalize<<<dagr_div_up(cells, 4), 128, 0, (cudaStream_t)stream>>>(*parent, C, aggr, accmax, accsum, possum,
+                                                                                ptmax, pcnt, pxy, tmean, tmax, x);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// keep_temporal_ordering (pooling.py:69-72)
+__global__ void k_temporal_filter(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const float *__restrict__ tmax,
+                                  uint32_t *__restrict__ mask)
+{
+    const int cells = gr.B * gr.ny * gr.nx;
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= cells || cnt[cell] <= 0) return;
+    const int per = gr.ny * gr.nx;
+    const int b = cell / per, rem = cell % per, cy = rem / gr.nx, cx = rem % gr.nx;
+    uint32_t m = mask[cell], keep = 0;
+    for (int bit = 0; bit < 9; bit++) {
+        if (!((m >> bit) & 1u) || bit == 4) continue;
+        const int sx = cx + bit % 3 - 1, sy = cy + bit / 3 - 1;
+        if (sx < 0 || sy < 0 || sx >= gr.nx || sy >= gr.ny) continue;
+        const int src = b * per + sy * gr.nx + sx;
+        if (cnt[src] > 0 && tmax[cell] > tmax[src]) keep |= 1u << bit;
+    }
+    mask[cell] = keep;
+}
+
+extern "C" int dagr_grid_temporal_filter(const dagr_grid_t *gr, const int32_t *cnt, const float *tmax, uint32_t *mask,
+                                         void *stream)
+{
+    const int cells = gr->B * gr->ny * gr->nx;
+    k_temporal_filter<<<dagr_div_up(cells, 128), 128, 0, (cudaStream_t)stream>>>(*gr, cnt, tmax, mask);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// to_dense, decode, NMS
+// ------------------------------------------------------------------------------------------------
+__global__ void k_to_dense(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const float *__restrict__ x, int C,
+                           const float *__restrict__ add, float *__restrict__ dense, int64_t total)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int per = gr.ny * gr.nx;
+    const int xy = (int)(i % per);
+    const int c = (int)((i / per) % C);
+    const int b = (int)(i / ((int64_t)per * C));
+    const int64_t cell = (int64_t)b * per + xy;
+    float v = cnt[cell] > 0 ? x[cell * C + c] : 0.f;
+    if (add) v += add[i];
+    dense[i] = v;
+}
+
+extern "C" int dagr_grid_to_dense(const dagr_grid_t *gr, const int32_t *cnt, const float *x, int C, const float *add,
+                                  float *dense, void *stream)
+{
+    const int64_t total = (int64_t)gr->B * C * gr->ny * gr->nx;
+    k_to_dense<<<dagr_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(*gr, cnt, x, C, add, dense, total);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+__global__ void k_head_decode(const float *__restrict__ reg, const float *__restrict__ obj, const float *__restrict__ cls,
+                              int B, int nc, int h, int w, float stride, int a0, int A, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int hw = h * w;
+    if (i >= B * hw) return;
+    const int b = i / hw, a = i % hw, gy = a / w, gx = a % w;
+    float *o = out + ((int64_t)b * A + a0 + a) * (5 + nc);
+    const float *r = reg + (int64_t)b * 4 * hw + a;
+    o[0] = (r[0] + (float)gx) * stride;
+    o[1] = (r[hw] + (float)gy) * stride;
+    o[2] = expf(r[2 * hw]) * stride;
+    o[3] = expf(r[3 * hw]) * stride;
+    o[4] = 1.f / (1.f + expf(-obj[(int64_t)b * hw + a]));
+    for (int c = 0; c < nc; c++) o[5 + c] = 1.f / (1.f + expf(-cls[((int64_t)b * nc + c) * hw + a]));
+}
+
+extern "C" int dagr_head_decode(const float *reg, const float *obj, const float *cls, int B, int nc, int h, int w,
+                                int stride, int a0, int A, float *out, void *stream)
+{
+    k_head_decode<<<dagr_div_up((int64_t)B * h * w, 128), 128, 0, (cudaStream_t)stream>>>(reg, obj, cls, B, nc, h, w,
+                                                                                       (float)stride, a0, A, out);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+#define NMS_MAX 1024
+__global__ void __launch_bounds__(256)
+k_postprocess_nms(const float *__restrict__ pred, int A, int nc, float conf_thre, float nms_thre, float max_dim1,
+                  int filtering, float *__restrict__ det, int32_t *__restrict__ ndet)
+{
+    __shared__ float bx[NMS_MAX][4];     // class-offset boxes used for IoU
+    __shared__ float sc[NMS_MAX];
+    __shared__ short order[NMS_MAX];     // candidate ids in descending score order
+    __shared__ unsigned char alive[NMS_MAX];
+    __shared__ int ncand;
+    const int b = blockIdx.x;
+    const float *P = pred + (int64_t)b * A * (5 + nc);
+    float *D = det + (int64_t)b * A * 6;
+    if (threadIdx.x == 0) ncand = 0;
+    __syncthreads();
+    // per anchor: xyxy, class max, score, confidence mask (model/utils.py:62-87)
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        const float *p = P + (int64_t)a * (5 + nc);
+        const float x1 = p[0] - p[2] / 2.f, y1 = p[1] - p[3] / 2.f;
+        const float x2 = p[2] + x1, y2 = p[3] + y1;
+        float cc = p[5]; int cl = 0;
+        for (int c = 1; c < nc; c++) if (p[5 + c] > cc) { cc = p[5 + c]; cl = c; }
+        const float score = p[4] * cc;
+        const bool keep = !filtering || (score * cc >= conf_thre);
+        // stash raw detection in the output slot a (compacted later)
+        D[a * 6 + 0] = x1; D[a * 6 + 1] = y1; D[a * 6 + 2] = x2; D[a * 6 + 3] = y2;
+        D[a * 6 + 4] = score; D[a * 6 + 5] = (float)cl;
+        const float offs = (float)cl * max_dim1;
+        bx[a][0] = x1 + offs; bx[a][1] = y1 + offs; bx[a][2] = x2 + offs; bx[a][3] = y2 + offs;
+        sc[a] = score;
+        alive[a] = keep ? 1 : 0;
+    }
+    __syncthreads();
+    if (!filtering) { if (threadIdx.x == 0) ndet[b] = A; return; }
+    // rank among kept candidates: descending score, ties by anchor index
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        if (!alive[a]) continue;
+        int r = 0;
+        const float s = sc[a];
+        for (int j = 0; j < A; j++) if (alive[j] && (sc[j] > s || (sc[j] == s && j < a))) r++;
+        order[r] = (short)a;
+        atomicAdd(&ncand, 1);
+    }
+    __syncthreads();
+    const int n = ncand;
+    // greedy suppression in score order (torchvision.ops.nms semantics)
+    for (int i = 0; i < n; i++) {
+        const int ai = order[i];
+        if (alive[ai]) {                                    // uniform across the block (shared)
+            const float ax1 = bx[ai][0], ay1 = bx[ai][1], ax2 = bx[ai][2], ay2 = bx[ai][3];
+            const float sa = (ax2 - ax1) * (ay2 - ay1);
+            for (int k = i + 1 + threadIdx.x; k < n; k += blockDim.x) {
+                const int aj = order[k];
+                if (!alive[aj]) continue;
+                const float l = fmaxf(ax1, bx[aj][0]), t = fmaxf(ay1, bx[aj][1]);
+                const float r = fminf(ax2, bx[aj][2]), bt = fminf(ay2, bx[aj][3]);
+                const float iw = fmaxf(r - l, 0.f), ih = fmaxf(bt - t, 0.f);
+                const float inter = iw * ih;
+                const float sb = (bx[aj][2] - bx[aj][0]) * (bx[aj][3] - bx[aj][1]);
+                if (inter / (sa + sb - inter) > nms_thre) alive[aj] = 0;
+            }
+        }
+        __syncthreads();
+    }
+    // compact survivors in score order; stage through shared (reuse bx rows as 6-float records is too small) ->
+    // serial compaction by one warp keeps it simple (A <= 1024)
+    __shared__ float stage[NMS_MAX][6];
+    __shared__ int nout;
+    if (threadIdx.x == 0) {
+        int m = 0;
+        for (int i = 0; i < n; i++) {
+            const int a = order[i];
+            if (alive[a]) { for (int k = 0; k < 6; k++) stage[m][k] = D[a * 6 + k]; m++; }
+        }
+        nout = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < A * 6; i += blockDim.x) D[i] = (i / 6 < nout) ? stage[i / 6][i % 6] : 0.f;
+    if (threadIdx.x == 0) ndet[b] = nout;
+}
+
+extern "C" int dagr_postprocess_nms(const float *pred, int B, int A, int nc, float conf_thre, float nms_thre, int width,
+                                    int height, int filtering, float *det, int32_t *ndet, void *stream)
+{
+    DAGR_CHECK_ARG(A > 0 && A <= NMS_MAX, "A must be in [1,1024]");
+    const float max_dim1 = (float)((width > height ? width : height) + 1);
+    k_postprocess_nms<<<B, 256, 0, (cudaStream_t)stream>>>(pred, A, nc, conf_thre, nms_thre, max_dim1, filtering, det, ndet);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a8 sample_features: 3-D bilinear grid_sample, align_corners=True, zero padding (net.py:193-221)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sample_features(const float *__restrict__ img, int Bi, int C, int h, int w,
+                                  const float *__restrict__ posx, const float *__restrict__ posy,
+                                  const int32_t *__restrict__ bidx, int64_t n, float width, float height,
+                                  float *__restrict__ out, int ldo, int c0)
+{
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    // normalise exactly as _sample_features does, then unnormalise as grid_sample(align_corners=True)
+    float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fmul_rn(posx[i], width)), width - 1.f), 1.f);
+    float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fmul_rn(posy[i], height)), height - 1.f), 1.f);
+    const float bs = (float)(Bi > 1 ? Bi : 2);
+    float gz = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, (float)bidx[i]), bs - 1.f), 1.f);
+    const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(w - 1));
+    const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(h - 1));
+    const float iz = __fmul_rn(__fmul_rn(__fadd_rn(gz, 1.f), 0.5f), (float)(Bi - 1));
+    const float x0f = floorf(ix), y0f = floorf(iy), z0f = floorf(iz);
+    const int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
+    const float tx = ix - x0f, ty = iy - y0f, tz = iz - z0f;
+    for (int c = lane; c < C; c += 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int dz = 0; dz < 2; dz++) {
+            const int z = z0 + dz;
+            const float wz = dz ? tz : 1.f - tz;
+            if (z < 0 || z >= Bi) continue;
+#pragma unroll
+            for (int dy = 0; dy < 2; dy++) {
+                const int y = y0 + dy;
+                const float wy = dy ? ty : 1.f - ty;
+                if (y < 0 || y >= h) continue;
+#pragma unroll
+                for (int dx = 0; dx < 2; dx++) {
+                    const int x = x0 + dx;
+                    const float wx = dx ? tx : 1.f - tx;
+                    if (x < 0 || x >= w) continue;
+                    acc += img[(((int64_t)z * C + c) * h + y) * w + x] * (wx * wy * wz);
+                }
+            }
+        }
+        out[i * ldo + c0 + c] = acc;
+    }
+}
+
+extern "C" int dagr_sample_features(const float *img, int Bi, int C, int h, int w, const float *posx, const float *posy,
+                                    const int32_t *bidx, int64_t n, int width, int height, float *out, int ldo, int c0,
+                                    void *stream)
+{
+    if (n <= 0) return DAGR_OK;
+    k_sample_features<<<dagr_div_up(n, 4), 128, 0, (cudaStream_t)stream>>>(img, Bi, C, h, w, posx, posy, bidx, n,
+                                                                         (float)width, (float)height, out, ldo, c0);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}

@@ -1,0 +1,69 @@
+// common.cuh -- shared helpers for libdagr_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/dagr_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define DAGR_HOST 1
+#endif
+
+void dagr_set_error(const char *fmt, ...);
+
+#define DAGR_CHECK_ARG(cond, msg)                                              \
+    do { if (!(cond)) { dagr_set_error("%s: %s", __func__, msg); return DAGR_E_ARG; } } while (0)
+
+#define DAGR_CHECK_LAUNCH()                                                    \
+    do { cudaError_t e__ = cudaGetLastError();                                 \
+         if (e__ != cudaSuccess) { dagr_set_error("%s: %s", __func__, cudaGetErrorString(e__)); \
+                                   return DAGR_E_CUDA; } } while (0)
+
+#define DAGR_CUDA(call)                                                        \
+    do { cudaError_t e__ = (call);                                             \
+         if (e__ != cudaSuccess) { dagr_set_error("%s: %s", __func__, cudaGetErrorString(e__)); \
+                                   return DAGR_E_CUDA; } } while (0)
+
+static inline int dagr_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// order-preserving float <-> uint32 encoding (0 is below every encoded value -> "empty")
+__device__ __forceinline__ uint32_t enc_ordered(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(uint32_t e)
+{
+    uint32_t u = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
+    return __uint_as_float(u);
+}
+
+// Blackwell packed fp32x2 FMA (SASS FFMA2): d = a*b + c on both halves.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// degree-1 open B-spline basis in 2-D (torch_spline_conv semantics): 4 (weight, slot) pairs
+// for pseudo coordinates (ax, ay); kernel_size ks per dim.
+__device__ __forceinline__ void spline_basis2(float ax, float ay, int ks, float w[4], int slot[4])
+{
+    float vx = ax * (float)(ks - 1), vy = ay * (float)(ks - 1);
+    float fx = vx - floorf(vx), fy = vy - floorf(vy);
+    int ix = (int)vx, iy = (int)vy;                 // C-cast truncation like the reference
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        int kx = s & 1, ky = (s >> 1) & 1;
+        int sx = (ix + kx) % ks, sy = (iy + ky) % ks;
+        if (sx < 0) sx += ks;
+        if (sy < 0) sy += ks;
+        slot[s] = sx + ks * sy;
+        // basis *= k ? frac : 1-frac, x first then y (same association as the reference loop)
+        w[s] = (kx ? fx : 1.f - fx) * (ky ? fy : 1.f - fy);
+    }
+}

@@ -1,0 +1,395 @@
+"""Host-side driver of the hot path: reads the nn.Module tree's tensors, owns geometry tables and
+workspaces, and enqueues the sm_100a kernels of libdagr_b200.so on the current CUDA stream.
+
+Call sequence mirrors Net.forward / GNNHead.forward (src/dagr/model/networks/net.py:108-190,
+dagr.py:192-312) but the event level is fused (graph sort -> probe -> conv_a -> conv_b+pool1) and the
+coarse levels run on dense voxel grids.  No host synchronisation happens inside `forward_events`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from .geometry import Geometry
+
+
+def _fold_bn(bn):
+    m = bn.module
+    scale = (m.weight / torch.sqrt(m.running_var + m.eps)).float()
+    shift = (m.bias - m.running_mean * scale).float()
+    return scale.contiguous(), shift.contiguous()
+
+
+def _fill(arr, t: torch.Tensor):
+    flat = t.detach().float().cpu().contiguous().view(-1)
+    assert flat.numel() == len(arr), (flat.numel(), len(arr))
+    C.memmove(arr, flat.data_ptr(), flat.numel() * 4)
+
+
+class _ConvPack:
+    def __init__(self, conv, norm=None, relu=False, dev=None):
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        self.weight = conv.weight.detach().float().contiguous().to(dev)
+        self.rootT = conv.lin.weight.detach().float().t().contiguous().to(dev)
+        self.bias = conv.bias.detach().float().contiguous().to(dev) if conv.bias is not None else None
+        if norm is not None:
+            s, b = _fold_bn(norm)
+            self.scale, self.shift = s.detach().to(dev), b.detach().to(dev)
+        else:
+            self.scale = self.shift = None
+        self.relu = relu
+
+
+class _LayerPack:
+    def __init__(self, layer, relu, dev):
+        self.a = _ConvPack(layer.conv_block1.conv, layer.conv_block1.norm, relu, dev)
+        self.b = _ConvPack(layer.conv_block2.conv, layer.conv_block2.norm, relu, dev)
+        self.skipT = layer.conv_block2.lin.mlp.weight.detach().float().t().contiguous().to(dev)
+        s, b = _fold_bn(layer.conv_block2.norm_skip)
+        self.sscale, self.sshift = s.detach().to(dev), b.detach().to(dev)
+
+
+class GridState:
+    """one voxel-grid level: valid count, rounded pixel position, t statistics, in-edge mask, features."""
+
+    def __init__(self, level, cells, dev):
+        self.level = level
+        self.cells = cells
+        self.cnt = torch.empty(cells, dtype=torch.int32, device=dev)
+        self.pxy = torch.empty((cells, 2), dtype=torch.int32, device=dev)
+        self.tmean = torch.empty(cells, dtype=torch.float32, device=dev)
+        self.tmax = torch.empty(cells, dtype=torch.float32, device=dev)
+        self.mask = None
+        self.x = None
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.lib = _lib.load()
+        self._geoms: Dict[tuple, Geometry] = {}
+        self._pack = None
+        self._pack_key = None
+        self._ws: Dict[tuple, dict] = {}
+        self.keep_node_features = False      # debug / parity: materialise per-event activations
+        self.last = {}
+
+    # ------------------------------------------------------------------------------------------
+    def geometry(self, W, H, B, device) -> Geometry:
+        key = (int(W), int(H), int(B), str(device))
+        g = self._geoms.get(key)
+        if g is None:
+            a = self.model.args
+            g = Geometry(W, H, B, radius=a.radius, time_window=self.model.time_window,
+                         max_neighbors=a.max_neighbors, max_queue_size=self.model.backbone.events_to_graph.max_queue_size,
+                         pooling_dim_at_output=a.pooling_dim_at_output, kernel_size=getattr(a, "kernel_size", 5),
+                         device=device)
+            self._geoms[key] = g
+        return g
+
+    def _params_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.state_dict().values())
+
+    def pack(self, geom: Geometry, device):
+        key = (self._params_key(), tuple(geom.slots1), str(device))
+        if self._pack is not None and self._pack_key == key:
+            return self._pack
+        m = self.model
+        bb, hd = m.backbone, m.head
+        act = getattr(m.args, "activation", "relu")
+        if act != "relu":
+            raise NotImplementedError("dagr_b200 kernels implement activation=relu (all reference configs)")
+        relu = True
+        l1 = bb.conv_block1
+        ca, cb = l1.conv_block1, l1.conv_block2
+        if ca.conv.in_channels != 3 or ca.conv.out_channels != 16:
+            raise NotImplementedError("event-level fast path expects conv_block1 = Layer(3 -> 16) "
+                                      "(events only, base_width 0.5)")
+        slots = torch.tensor(geom.slots1, dtype=torch.long)
+        pa = _lib.L1AParams()
+        _fill(pa.w, ca.conv.weight.detach().cpu()[slots])                    # [15,3,16]
+        _fill(pa.root, ca.conv.lin.weight.detach().cpu().t())               # [3,16]
+        s, b = _fold_bn(ca.norm); _fill(pa.scale, s); _fill(pa.shift, b)
+        pa.relu = 1
+        pb = _lib.L1BParams()
+        _fill(pb.w, cb.conv.weight.detach().cpu()[slots])                    # [15,16,16]
+        _fill(pb.root, cb.conv.lin.weight.detach().cpu().t())
+        _fill(pb.skip, cb.lin.mlp.weight.detach().cpu().t())                # [3,16]
+        s, b = _fold_bn(cb.norm); _fill(pb.scale, s); _fill(pb.shift, b)
+        s, b = _fold_bn(cb.norm_skip); _fill(pb.sscale, s); _fill(pb.sshift, b)
+        pb.relu = 1
+        pk = dict(l1a=pa, l1b=pb)
+        pk["layers"] = [_LayerPack(getattr(bb, n), relu, device) for n in ("layer2", "layer3", "layer4", "layer5")]
+        heads = []
+        for k in range(hd.num_scales):
+            sfx = str(k + 1)
+            stem, cc, rc = getattr(hd, "stem" + sfx), getattr(hd, "cls_conv" + sfx), getattr(hd, "reg_conv" + sfx)
+            heads.append(dict(stem=_ConvPack(stem.conv, stem.norm, relu, device),
+                              cls_conv=_ConvPack(cc.conv, cc.norm, relu, device),
+                              reg_conv=_ConvPack(rc.conv, rc.norm, relu, device),
+                              cls_pred=_ConvPack(getattr(hd, "cls_pred" + sfx), None, False, device),
+                              reg_pred=_ConvPack(getattr(hd, "reg_pred" + sfx), None, False, device),
+                              obj_pred=_ConvPack(getattr(hd, "obj_pred" + sfx), None, False, device)))
+        pk["heads"] = heads
+        self._pack, self._pack_key = pk, key
+        return pk
+
+    # ------------------------------------------------------------------------------------------
+    def workspace(self, geom: Geometry, N: int, device):
+        key = (id(geom), str(device))
+        ws = self._ws.get(key)
+        cap = 0 if ws is None else ws["cap"]
+        if ws is None or N > cap:
+            cap = max(int(N * 1.25), 1024)
+            dev = device
+            nscan = max(geom.NK + 1, cap + 1)
+            ws = dict(cap=cap)
+            ws["key"] = torch.empty(cap, dtype=torch.int32, device=dev)
+            ws["tmp"] = torch.empty(cap, dtype=torch.int32, device=dev)
+            ws["count"] = torch.zeros(geom.NK + 1, dtype=torch.int32, device=dev)
+            ws["blocksums"] = torch.empty(int(self.lib.dagr_scan_blocks(nscan)) + 2, dtype=torch.int32, device=dev)
+            ws["start"] = torch.empty(geom.NK + 1, dtype=torch.int32, device=dev)
+            ws["perm"] = torch.empty(cap, dtype=torch.int32, device=dev)
+            ws["ti"] = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+            ws["xyb"] = torch.empty(cap, dtype=torch.int32, device=dev)
+            ws["feat_s"] = torch.empty(cap, dtype=torch.float32, device=dev)
+            ws["nbr"] = torch.empty(_lib.ELL * cap, dtype=torch.int32, device=dev)
+            ws["off"] = torch.empty(_lib.ELL * cap, dtype=torch.int16, device=dev)
+            ws["xa"] = torch.empty((cap, 16), dtype=torch.float32, device=dev)
+            ws["x1"] = None
+            # zero-on-entry accumulators of all levels in ONE buffer (single memset per forward)
+            C_lv = self.model.backbone.output_channels          # [16, 64, C, C, C]
+            sizes = {}
+            off = 0
+
+            def take(name, nbytes):
+                nonlocal off
+                nbytes = (nbytes + 255) // 256 * 256
+                sizes[name] = (off, nbytes)
+                off += nbytes
+
+            take("cellmask", geom.cells1 * 4)
+            take("poolmax", geom.cells1 * 16 * 4)
+            for lv in (1, 2, 3):
+                cells = geom.cells(lv)
+                Cc = C_lv[lv] + 64 * 3                          # channels pooled into this level (+ headroom for image features)
+                take(f"acc{lv}", cells * Cc * 8)
+                take(f"possum{lv}", cells * 3 * 8)
+                take(f"ptmax{lv}", cells * 4)
+                take(f"pcnt{lv}", cells * 4)
+                take(f"pmask{lv}", cells * 4)
+            take("err", 4)
+            ws["zero_buf"] = torch.zeros(off, dtype=torch.uint8, device=dev)
+            ws["zero_slices"] = sizes
+            grids = []
+            for lv in range(4):
+                grids.append(GridState(lv, geom.cells(lv), dev))
+            ws["grids"] = grids
+            ws["pool"] = {}
+            self._ws[key] = ws
+        return ws
+
+    def _zs(self, ws, name, dtype):
+        off, nbytes = ws["zero_slices"][name]
+        return ws["zero_buf"][off:off + nbytes].view(dtype)
+
+    def _buf(self, ws, name, shape, dtype, dev):
+        t = ws["pool"].get(name)
+        n = 1
+        for s in shape:
+            n *= s
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=dev)
+            ws["pool"][name] = t
+        return t[:n].view(*shape)
+
+    # ------------------------------------------------------------------------------------------
+    def _grid_conv(self, geom, lv, gs: GridState, xin, pack: _ConvPack, skip, out, st):
+        level = geom.levels[lv]
+        _lib.check(self.lib.dagr_grid_conv(C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.mask),
+                                           _lib.ptr(xin), pack.cin, pack.cout, _lib.ptr(pack.weight), _lib.ptr(pack.rootT),
+                                           _lib.ptr(pack.bias), _lib.ptr(pack.scale), _lib.ptr(pack.shift),
+                                           _lib.ptr(skip), 1 if pack.relu else 0, level.den_x, level.den_y,
+                                           _lib.ptr(out), st), "grid_conv")
+
+    def _layer(self, geom, lv, gs: GridState, lp: _LayerPack, ws, name, st, dev):
+        level = geom.levels[lv]
+        cells = gs.cells
+        cx = gs.x.shape[1]
+        xin = self._buf(ws, name + "_in", (cells, cx + 2), torch.float32, dev)
+        _lib.check(self.lib.dagr_grid_cat_pos(C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.x), cx,
+                                              _lib.ptr(xin), st), "cat_pos")
+        a = self._buf(ws, name + "_a", (cells, lp.a.cout), torch.float32, dev)
+        self._grid_conv(geom, lv, gs, xin, lp.a, None, a, st)
+        sk = self._buf(ws, name + "_s", (cells, lp.b.cout), torch.float32, dev)
+        _lib.check(self.lib.dagr_grid_linear_bn(cells, _lib.ptr(gs.cnt), _lib.ptr(xin), cx + 2, lp.b.cout,
+                                                _lib.ptr(lp.skipT), _lib.ptr(lp.sscale), _lib.ptr(lp.sshift),
+                                                _lib.ptr(sk), st), "linear_bn")
+        out = self._buf(ws, name + "_o", (cells, lp.b.cout), torch.float32, dev)
+        self._grid_conv(geom, lv, gs, a, lp.b, sk, out, st)
+        return xin, a, out
+
+    def _pool(self, geom, lv_child, gc: GridState, x, aggr, ws, st, dev, keep_temporal):
+        """pool level lv_child (0-based) into lv_child+1."""
+        lp = lv_child + 1
+        child, parent = geom.levels[lv_child], geom.levels[lp]
+        gp: GridState = ws["grids"][lp]
+        Cc = x.shape[1]
+        acc = self._zs(ws, f"acc{lp}", torch.uint8)
+        accmax = acc.view(torch.int32) if aggr == 0 else None
+        accsum = acc.view(torch.float64) if aggr == 1 else None
+        possum = self._zs(ws, f"possum{lp}", torch.float64)
+        ptmax = self._zs(ws, f"ptmax{lp}", torch.int32)
+        pcnt = self._zs(ws, f"pcnt{lp}", torch.int32)
+        pmask = self._zs(ws, f"pmask{lp}", torch.int32)
+        err = self._zs(ws, "err", torch.int32)
+        _lib.check(self.lib.dagr_grid_pool(C.byref(child.grid), C.byref(parent.grid), _lib.ptr(parent.cellx_dev),
+                                           _lib.ptr(parent.celly_dev), _lib.ptr(gc.cnt), _lib.ptr(gc.pxy),
+                                           _lib.ptr(gc.tmean), _lib.ptr(gc.tmax), _lib.ptr(gc.mask), _lib.ptr(x), Cc, aggr,
+                                           _lib.ptr(accmax), _lib.ptr(accsum), _lib.ptr(possum), _lib.ptr(ptmax),
+                                           _lib.ptr(pcnt), _lib.ptr(pmask), _lib.ptr(err), st), "grid_pool")
+        gp.x = self._buf(ws, f"gx{lp}", (gp.cells, Cc), torch.float32, dev)
+        _lib.check(self.lib.dagr_grid_pool_finalize(C.byref(parent.grid), Cc, aggr, _lib.ptr(accmax), _lib.ptr(accsum),
+                                                    _lib.ptr(possum), _lib.ptr(ptmax), _lib.ptr(pcnt), _lib.ptr(gp.pxy),
+                                                    _lib.ptr(gp.tmean), _lib.ptr(gp.tmax), _lib.ptr(gp.x), st),
+                   "grid_pool_finalize")
+        gp.cnt = pcnt[:gp.cells]
+        gp.mask = pmask[:gp.cells]
+        if keep_temporal:
+            _lib.check(self.lib.dagr_grid_temporal_filter(C.byref(parent.grid), _lib.ptr(gp.cnt), _lib.ptr(gp.tmax),
+                                                          _lib.ptr(gp.mask), st), "temporal_filter")
+        return gp
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_events(self, batch_i32: torch.Tensor, pos_i32: torch.Tensor, feat: torch.Tensor, B: int,
+                       W: int, H: int, image_outs=None):
+        """batch int32[N], pos int32[N,3], feat fp32[N] (polarity) on CUDA -> decoded [B, A, 5+nc]."""
+        for n, t in (("batch", batch_i32), ("pos", pos_i32), ("x", feat)):
+            _lib.require_cuda(t, n)
+        dev = pos_i32.device
+        N = int(batch_i32.shape[0])
+        geom = self.geometry(W, H, B, dev)
+        pk = self.pack(geom, dev)
+        ws = self.workspace(geom, N, dev)
+        st = _lib.stream_ptr()
+        lib = self.lib
+        g = C.byref(geom.c_geom)
+        model = self.model
+        kto = bool(getattr(model.args, "keep_temporal_ordering", False))
+
+        ws["zero_buf"].zero_()
+        nbr, off = ws["nbr"], ws["off"]
+        cellmask = self._zs(ws, "cellmask", torch.int32)
+        poolmax = self._zs(ws, "poolmax", torch.int32)
+        # ---- event level ---------------------------------------------------------------------
+        _lib.check(lib.dagr_graph_sort(g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ws["key"]),
+                                       _lib.ptr(ws["tmp"]), _lib.ptr(ws["count"]), _lib.ptr(ws["blocksums"]),
+                                       _lib.ptr(ws["start"]), _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
+                                       _lib.ptr(ws["feat_s"]), st), "graph_sort")
+        _lib.check(lib.dagr_graph_search(g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
+                                         _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(cellmask), st), "graph_search")
+        _lib.check(lib.dagr_l1_conv_a(g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(nbr), _lib.ptr(off),
+                                      _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(ws["xa"]), st), "l1_conv_a")
+        x1 = None
+        if self.keep_node_features:
+            if ws["x1"] is None or ws["x1"].shape[0] < ws["cap"]:
+                ws["x1"] = torch.empty((ws["cap"], 16), dtype=torch.float32, device=dev)
+            x1 = ws["x1"]
+        _lib.check(lib.dagr_l1_conv_b_pool(g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]),
+                                           _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]),
+                                           _lib.ptr(x1), _lib.ptr(poolmax), st), "l1_conv_b_pool")
+        g1: GridState = ws["grids"][0]
+        g1.x = self._buf(ws, "gx0", (g1.cells, 16), torch.float32, dev)
+        _lib.check(lib.dagr_pool1_finalize(g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(ws["ti"]),
+                                           _lib.ptr(poolmax), 16, _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean),
+                                           _lib.ptr(g1.tmax), _lib.ptr(g1.x), st), "pool1_finalize")
+        g1.mask = cellmask[:g1.cells]
+        if kto:
+            _lib.check(lib.dagr_grid_temporal_filter(C.byref(geom.levels[0].grid), _lib.ptr(g1.cnt), _lib.ptr(g1.tmax),
+                                                     _lib.ptr(g1.mask), st), "temporal_filter")
+        # ---- coarse levels -------------------------------------------------------------------
+        aggr_cfg = 0 if getattr(model.args, "pooling_aggr", "max") == "max" else 1
+        lay = pk["layers"]
+        inter = {}
+        _, _, o2 = self._layer(geom, 0, g1, lay[0], ws, "layer2", st, dev)
+        g2 = self._pool(geom, 0, g1, o2, aggr_cfg, ws, st, dev, kto)
+        _, _, o3 = self._layer(geom, 1, g2, lay[1], ws, "layer3", st, dev)
+        g3 = self._pool(geom, 1, g2, o3, aggr_cfg, ws, st, dev, kto)
+        _, _, o4 = self._layer(geom, 2, g3, lay[2], ws, "layer4", st, dev)           # out3
+        g4 = self._pool(geom, 2, g3, o4, 1, ws, st, dev, kto)                        # pool4 is always mean (net.py:96-97)
+        _, _, o5 = self._layer(geom, 3, g4, lay[3], ws, "layer5", st, dev)           # out4
+        inter.update(o2=o2, o3=o3, o4=o4, o5=o5)
+        # ---- head ----------------------------------------------------------------------------
+        nc = model.backbone.num_classes
+        scales = [(2, g3, o4), (3, g4, o5)][-model.head.num_scales:]
+        A = sum(geom.levels[lv].nx * geom.levels[lv].ny for lv, _, _ in scales)
+        out = self._buf(ws, "decoded", (B, A, 5 + nc), torch.float32, dev)
+        a0 = 0
+        dense_all = []
+        for k, (lv, gs, xo) in enumerate(scales):
+            hp = pk["heads"][k]
+            level = geom.levels[lv]
+            cells = gs.cells
+            nm = f"head{k}"
+            stem = self._buf(ws, nm + "_stem", (cells, hp["stem"].cout), torch.float32, dev)
+            self._grid_conv(geom, lv, gs, xo, hp["stem"], None, stem, st)
+            cf = self._buf(ws, nm + "_cf", (cells, hp["cls_conv"].cout), torch.float32, dev)
+            rf = self._buf(ws, nm + "_rf", (cells, hp["reg_conv"].cout), torch.float32, dev)
+            self._grid_conv(geom, lv, gs, stem, hp["cls_conv"], None, cf, st)
+            self._grid_conv(geom, lv, gs, stem, hp["reg_conv"], None, rf, st)
+            dense = {}
+            for name, src, cpk in (("cls", cf, hp["cls_pred"]), ("reg", rf, hp["reg_pred"]), ("obj", rf, hp["obj_pred"])):
+                o = self._buf(ws, nm + "_" + name, (cells, cpk.cout), torch.float32, dev)
+                self._grid_conv(geom, lv, gs, src, cpk, None, o, st)
+                d = self._buf(ws, nm + "_d" + name, (B, cpk.cout, level.ny, level.nx), torch.float32, dev)
+                add = None
+                if image_outs is not None:
+                    add = image_outs[name + "_output"][k].float().contiguous()
+                _lib.check(lib.dagr_grid_to_dense(C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(o), cpk.cout,
+                                                  _lib.ptr(add), _lib.ptr(d), st), "to_dense")
+                dense[name] = d
+            stride = model.backbone.strides[k]
+            _lib.check(lib.dagr_head_decode(_lib.ptr(dense["reg"]), _lib.ptr(dense["obj"]), _lib.ptr(dense["cls"]), B, nc,
+                                            level.ny, level.nx, int(stride), a0, A, _lib.ptr(out), st), "head_decode")
+            a0 += level.nx * level.ny
+            dense_all.append(dense)
+        self.last = dict(geom=geom, ws=ws, N=N, grids=[g1, g2, g3, g4], inter=inter, dense=dense_all, x1=x1)
+        return out
+
+    @torch.no_grad()
+    def postprocess(self, decoded: torch.Tensor, conf_thre, nms_thre, width, height, filtering=True):
+        """postprocess_network_output on device (model/utils.py:61-110): det [B,A,6], ndet [B]."""
+        B, A, D = decoded.shape
+        nc = D - 5
+        dev = decoded.device
+        det = torch.empty((B, A, 6), dtype=torch.float32, device=dev)
+        ndet = torch.empty(B, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.dagr_postprocess_nms(_lib.ptr(decoded), B, A, nc, float(conf_thre), float(nms_thre), int(width),
+                                                 int(height), 1 if filtering else 0, _lib.ptr(det), _lib.ptr(ndet),
+                                                 _lib.stream_ptr()), "postprocess_nms")
+        return det, ndet
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def export_edges(self):
+        """edge_index int64[2,E] in the reference's layout for the last forward (host sync)."""
+        L = self.last
+        geom, ws, N = L["geom"], L["ws"], L["N"]
+        dev = ws["perm"].device
+        if N == 0:
+            return torch.zeros((2, 0), dtype=torch.long, device=dev)
+        cap = geom.K * N
+        inv = torch.empty(N, dtype=torch.int32, device=dev)
+        rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        es = torch.empty(cap, dtype=torch.int64, device=dev)
+        ed = torch.empty(cap, dtype=torch.int64, device=dev)
+        _lib.check(self.lib.dagr_graph_export(C.byref(geom.c_geom), N, _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]),
+                                              _lib.ptr(ws["nbr"]), _lib.ptr(inv), _lib.ptr(rowptr), _lib.ptr(ws["blocksums"]),
+                                              _lib.ptr(es), _lib.ptr(ed), cap, _lib.stream_ptr()), "graph_export")
+        E = int(rowptr[N].item())
+        return torch.stack([es[:E], ed[:E]])

@@ -1,0 +1,230 @@
+/*
+ * dagr_b200.h -- C-ABI of libdagr_b200.so (hand-written sm_100a CUDA kernels for DAGR's hot path).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library never allocates, never synchronises and never throws: callers own all
+ *     buffers (workspace sizes are documented per call), every call only enqueues kernels
+ *     on `stream` (a cudaStream_t passed as void*) and returns 0 or a negative code
+ *     (DAGR_E_*); dagr_last_error() returns the message of the last failure on this thread;
+ *   - node order: after dagr_graph_sort the event level lives in "cell-major sorted order"
+ *     (position p); `perm[p]` is the arrival index the reference uses as node id.
+ *
+ * Each entry point cites the reference interface it replaces (paths under uzh-rpg/dagr).
+ */
+#ifndef DAGR_B200_H
+#define DAGR_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAGR_ABI_VERSION 1
+
+#define DAGR_OK            0
+#define DAGR_E_ARG        -1   /* bad argument / unsupported shape        */
+#define DAGR_E_CUDA       -2   /* CUDA launch or runtime error            */
+#define DAGR_E_UNSUPPORTED -3
+
+#define DAGR_ELL 16            /* neighbour slots per node (K-1 = 15 used, slot 15 = degree) */
+#define DAGR_KU  15            /* spline kernel slots reachable at the event level (3 x 5)   */
+#define DAGR_TABW 16           /* row stride (floats) of the offset->slot-weight table       */
+
+int         dagr_abi_version(void);
+const char *dagr_last_error(void);
+
+/* Geometry of one (width,height,batch,radius) configuration; tables are built on the host with
+ * the same fp32 torch ops the reference uses (dagr_b200/geometry.py) and uploaded once. */
+typedef struct {
+    int32_t W, H, B, T;            /* sensor size, samples per batch, time window (us)               */
+    int32_t r, ncell;              /* r = int(radius*W+1), ncell = (2r+1)^2   (ev_tgn.py:29)          */
+    int32_t dt_us, K, Q;           /* int(radius*T), max_neighbors, max_queue_size (ev_tgn.py:22-28) */
+    int32_t nx1, ny1;              /* pool1 voxel grid (pooling.py:56)                               */
+    int32_t CW, CH, CP;            /* padded cell extent in pixels, CP = CW*CH                       */
+    int32_t NK;                    /* number of sort keys = B*ny1*nx1*CP                             */
+    const int32_t *xkey;           /* [W]  cx*CP + (x - x0[cx])                                      */
+    const int32_t *ykey;           /* [H]  cy*nx1*CP + (y - y0[cy])*CW                               */
+    const int8_t  *spiral;         /* [ncell][2] spiral probe order (spiral.h:1-16)                  */
+    const float   *posx0;          /* [W]  fl(x / W)  (buffers.py:43)                                */
+    const float   *posy0;          /* [H]  fl(y / H)                                                 */
+} dagr_geom_t;
+
+/* ---------------------------------------------------------------------------------------------
+ * a1'  denormalize_pos  (src/dagr/model/layers/ev_tgn.py:11-16):  (pos*[W,H,T] + 1e-3).int()
+ * ------------------------------------------------------------------------------------------- */
+int dagr_denormalize_pos(const float *pos /*[N,3]*/, int64_t N, int W, int H, int T,
+                         int32_t *pos_i32 /*[N,3]*/, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2-a4  radius graph.  Replaces ev_graph_cuda.insert_in_queue_cuda + fill_edges_cuda
+ * (src/dagr/graph/ev_graph.cu:82-128,241-276) and their driver (graph/utils.py:6-23,
+ * ev_graph.py:63-103) for the reset=True forward.  Instead of a [B,Q,H,W] FIFO the events are
+ * counting-sorted by a cell-major pixel key; a pixel's FIFO column is the tail (newest Q) of its
+ * bin read backwards.
+ *
+ *   dagr_graph_sort   : batch i32[N], pos i32[N,3], feat f32[N] (polarity)  ->
+ *                       start i32[NK+1], perm i32[N], ti i32[N,2]=(t,arrival idx),
+ *                       xyb u32[N] = x | y<<12 | b<<24, feat_s f32[N]
+ *                       work: key i32[N], tmp i32[N], count i32[NK+1] (MUST be zero on entry; is
+ *                       zero again on exit), blocksums i32[dagr_scan_blocks(NK+1)+1]
+ *   dagr_graph_search : -> nbr i32[16,N] COLUMN-MAJOR ELL: slot q of node p at [q*N+p]; slots 0..14 =
+ *                       src positions in probe order, slot 15 = degree without the self loop;
+ *                       off u16[16,N] (spiral cell index of each neighbour, same layout), cellmask u32[B*ny1*nx1] (bit (dcy+1)*3+(dcx+1) set when some
+ *                       fine edge enters the cell from that neighbouring cell; MUST be zero on entry)
+ *   dagr_graph_export : -> edge_index i64[2,E] exactly as the reference returns it
+ *                       (dst ascending in arrival order, self loop first, then probe order);
+ *                       rowptr i32[N+1] is written too; E is left in rowptr[N].
+ *                       work: inv i32[N], blocksums as above (sized for N+1).
+ * ------------------------------------------------------------------------------------------- */
+int64_t dagr_scan_blocks(int64_t n);
+
+int dagr_graph_sort(const dagr_geom_t *g, const int32_t *batch, const int32_t *pos, const float *feat,
+                    int64_t N, int32_t *key, int32_t *tmp, int32_t *count, int32_t *blocksums,
+                    int32_t *start, int32_t *perm, int32_t *ti, uint32_t *xyb, float *feat_s,
+                    void *stream);
+
+int dagr_graph_search(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
+                      const uint32_t *xyb, int32_t *nbr, uint16_t *off, uint32_t *cellmask,
+                      void *stream);
+
+int dagr_graph_export(const dagr_geom_t *g, int64_t N, const int32_t *perm, const int32_t *ti,
+                      const int32_t *nbr, int32_t *inv, int32_t *rowptr, int32_t *blocksums,
+                      int64_t *edge_src /*[cap]*/, int64_t *edge_dst /*[cap]*/, int64_t cap,
+                      void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5-a7  event-level Layer (conv_block1): Cartesian attrs + MySplineConv (LUT form) + BN + act
+ * (src/dagr/model/layers/spline_conv.py:39-78, conv.py:10-72, components.py:9-35, net.py:122-126).
+ * `tab` f32[ncell][DAGR_TABW]: for spiral cell c the weights of the DAGR_KU reachable spline
+ * kernel slots (built from MySplineConv.init_lut's basis, spline_conv.py:27-35).
+ * Weights are passed by value (constant bank): slot-major  w[u][cin][cout].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    float w[DAGR_KU][3][16];      /* weight[slot_id[u]]  (Cin = polarity, x/W, y/H)  */
+    float root[3][16];            /* lin.weight^T                                    */
+    float scale[16], shift[16];   /* eval BN folded: g/sqrt(v+eps), b - m*scale      */
+    int32_t relu;                 /* args.activation == relu                         */
+} dagr_l1a_params_t;
+
+typedef struct {
+    float w[DAGR_KU][16][16];
+    float root[16][16];
+    float skip[3][16];            /* ConvBlockWithSkip.lin.mlp.weight^T             */
+    float scale[16], shift[16];   /* norm                                            */
+    float sscale[16], sshift[16]; /* norm_skip                                       */
+    int32_t relu;
+} dagr_l1b_params_t;
+
+int dagr_l1_conv_a(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, const float *feat_s,
+                   const int32_t *nbr, const uint16_t *off, const float *tab,
+                   const dagr_l1a_params_t *p_host, float *xa /*[N,16]*/, void *stream);
+
+/* conv_b + skip + activation, fused with pool1's per-voxel max (a9, pooling.py:74-75):
+ * poolmax u32[B*ny1*nx1][16] holds order-preserving encodings (0 = empty; MUST be zero on entry).
+ * x1 (optional, may be NULL) receives the per-node activations [N,16] in sorted order. */
+int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, const float *feat_s,
+                        const float *xa, const int32_t *nbr, const uint16_t *off, const float *tab,
+                        const dagr_l1b_params_t *p_host, float *x1, uint32_t *poolmax, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Coarse levels live on dense voxel grids [B, ny, nx]: per cell  valid, pixel position, features,
+ * and an 8-neighbour in-edge mask (bit (dcy+1)*3+(dcx+1), src cell = dst cell + (dcx,dcy)).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t nx, ny, B;             /* grid                                            */
+    int32_t W, H;                  /* sensor size                                     */
+    const float *posxr;            /* [W] fl(k * fl(1/W))  (pooling.py:47-49)         */
+    const float *posyr;            /* [H]                                             */
+} dagr_grid_t;
+
+/* a9 finalize of pool1: per voxel count / mean position (pool_pos) / round_to_pixel / decode max.
+ * out: cnt i32[cells], pxy i32[cells,2] (pixel coords after rounding), tmean f32[cells],
+ *      x f32[cells, C] (C = 16), cells = B*ny1*nx1.  One warp per voxel. */
+int dagr_pool1_finalize(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
+                        const int32_t *ti, const uint32_t *poolmax, int C,
+                        int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *x, void *stream);
+
+/* cat(x, pos[:, :2]) (net.py:135-136 etc.): xin[cells, Cx+2] */
+int dagr_grid_cat_pos(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const float *x,
+                      int Cx, float *xin, void *stream);
+
+/* a6 on a voxel grid: MySplineConv (basis form evaluated at the exact integer pixel offsets, which is
+ * what message_lut computes, spline_conv.py:39-47) + root + bias, then optional eval-BN, optional
+ * residual `skip` (already BN'd, [cells,Cout]) and optional relu -- i.e. ConvBlock / ConvBlockWithSkip
+ * (conv.py:10-56).
+ *   weight f32[25,Cin,Cout], rootT f32[Cin,Cout] (= lin.weight^T), bias f32[Cout]|NULL,
+ *   scale/shift f32[Cout]|NULL (folded eval BN)
+ *   attr = d/den + 0.5 with den_x = fl(2*M*W), den_y = fl(2*M*H)  (spline_conv.py:28-29)
+ */
+int dagr_grid_conv(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const uint32_t *mask,
+                   const float *xin, int Cin, int Cout, const float *weight, const float *rootT,
+                   const float *bias, const float *scale, const float *shift, const float *skip,
+                   int relu, float den_x, float den_y, float *out, void *stream);
+
+/* y = BN(x @ W^T) on valid cells (Linear + BatchNormData of ConvBlockWithSkip, conv.py:41-52);
+ * wT f32[Cin,Cout] */
+int dagr_grid_linear_bn(int64_t cells, const int32_t *cnt, const float *xin, int Cin, int Cout,
+                        const float *wT, const float *scale, const float *shift,
+                        float *out, void *stream);
+
+/* a9 on grids (pool2..4): scatter children into parent voxels. aggr: 0 = max, 1 = mean.
+ * cellx/celly: [W]/[H] pixel -> parent voxel index LUT (fp32-exact, geometry.py).
+ * accumulators (all MUST be zero on entry): accmax u32[cellsP*C] (aggr 0) | accsum f64[cellsP*C]
+ * (aggr 1), possum f64[cellsP,3], ptmax u32[cellsP], pcnt i32[cellsP], pmask u32[cellsP];
+ * err_flag i32[1] is set to 1 if a coarse edge would span more than one voxel. */
+int dagr_grid_pool(const dagr_grid_t *child, const dagr_grid_t *parent, const int32_t *cellx,
+                   const int32_t *celly, const int32_t *cnt, const int32_t *pxy, const float *tmean,
+                   const float *tmax, const uint32_t *mask, const float *x, int C, int aggr,
+                   uint32_t *accmax, double *accsum, double *possum, uint32_t *ptmax, int32_t *pcnt,
+                   uint32_t *pmask, int32_t *err_flag, void *stream);
+
+int dagr_grid_pool_finalize(const dagr_grid_t *parent, int C, int aggr, const uint32_t *accmax,
+                            const double *accsum, const double *possum, const uint32_t *ptmax,
+                            const int32_t *pcnt, int32_t *pxy, float *tmean, float *tmax, float *x,
+                            void *stream);
+
+/* keep_temporal_ordering (pooling.py:69-72): drop in-edges with t_max[dst] <= t_max[src] */
+int dagr_grid_temporal_filter(const dagr_grid_t *gr, const int32_t *cnt, const float *tmax,
+                              uint32_t *mask, void *stream);
+
+/* a10 to_dense (spline_conv.py:80-107): grid-major [cells, C] -> dense [B, C, ny, nx] (+= add, optional) */
+int dagr_grid_to_dense(const dagr_grid_t *gr, const int32_t *cnt, const float *x, int C,
+                       const float *add /*[B,C,ny,nx] or NULL*/, float *dense, void *stream);
+
+/* a11 collect_outputs + decode_outputs (dagr.py:292-312): per scale reg[B,4,h,w], obj[B,1,h,w],
+ * cls[B,nc,h,w] -> out[B, A, 5+nc] rows [a0, a0+h*w)  */
+int dagr_head_decode(const float *reg, const float *obj, const float *cls, int B, int nc, int h, int w,
+                     int stride, int a0, int A, float *out, void *stream);
+
+/* a11 postprocess_network_output + batched_nms_coordinate_trick (model/utils.py:25-33,61-110).
+ * pred f32[B,A,5+nc] (decoded, cxcywh) -> det f32[B,A,6] = (x1,y1,x2,y2,score,label) compacted in
+ * descending-score order, ndet i32[B].  One CTA per image, A <= 1024. */
+int dagr_postprocess_nms(const float *pred, int B, int A, int nc, float conf_thre, float nms_thre,
+                         int width, int height, int filtering, float *det, int32_t *ndet, void *stream);
+
+/* a8 sample_features (net.py:193-221): bilinear, align_corners=True, batch as depth.
+ * img f32[Bi,C,h,w]; positions given as normalised floats; out[n, ldo] columns [c0, c0+C) */
+int dagr_sample_features(const float *img, int Bi, int C, int h, int w, const float *posx, const float *posy,
+                         const int32_t *bidx, int64_t n, int width, int height, float *out, int ldo, int c0,
+                         void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a14  asy_tools (src/dagr/asynchronous/asy_tools/main.cu:239-244), same argument meaning.
+ * masked_isdiff writes kept[i] = idx[i] or -1 (the reference clobbers `indices` in place, :30-37);
+ * compaction is the caller's job exactly as in main.cu:124.
+ * ------------------------------------------------------------------------------------------- */
+int dagr_masked_lin(const int64_t *idx, int64_t K, const float *x_in, float *x_out, const float *weight,
+                    const float *bias /*or NULL*/, int Cin, int Cout, int add, void *stream);
+int dagr_masked_inplace_bn(const int64_t *idx, int64_t K, const float *x, float *x_out, const float *mean,
+                           const float *var, const float *weight, const float *bias, int C, float eps,
+                           void *stream);
+int dagr_masked_isdiff(int64_t *idx_inout, int64_t K, const float *a, const float *b, int C, float atol,
+                       float rtol, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAGR_B200_H */
