@@ -15,7 +15,7 @@ __global__ void k_masked_lin(const int64_t *__restrict__ idx, int64_t K, const f
     for (int co = lane; co < Cout; co += 32) {
         float acc = add ? x_out[r * Cout + co] : 0.f;
         const float *w = weight + (int64_t)co * Cin;
-        for (int ci = 0; ci < Cin; ci++) acc = __fadd_rn(acc, __fmul_rn(xi[ci], w[ci]));   // same order, no fma (main.cu:154-156)
+        for (int ci = 0; ci < Cin; ci++) acc = fmaf(xi[ci], w[ci], acc);   // same order as main.cu:154-156 (nvcc contracts it to FFMA there too)
         if (bias) acc = __fadd_rn(acc, bias[co]);
         x_out[r * Cout + co] = acc;
     }

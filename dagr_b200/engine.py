@@ -77,6 +77,32 @@ class Engine:
         self._ws: Dict[tuple, dict] = {}
         self.keep_node_features = False      # debug / parity: materialise per-event activations
         self.last = {}
+        self.launches = 0                    # kernels of libdagr_b200.so enqueued so far
+        self.prof = None                     # dict name -> [(start_evt, end_evt)] when per-op timing is on
+
+    # kernels enqueued by each C-ABI call (see csrc/*.cu)
+    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1,
+                     dagr_pool1_finalize=1, dagr_grid_cat_pos=1, dagr_grid_conv=1, dagr_grid_linear_bn=1, dagr_grid_pool=1,
+                     dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1,
+                     dagr_postprocess_nms=1, dagr_sample_features=1, dagr_denormalize_pos=1)
+
+    def _run(self, label, fn, *args):
+        if self.prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(fn(*args), label)
+        self.launches += self._NKERNELS.get(fn.__name__, 1)
+        if self.prof is not None:
+            e1.record()
+            self.prof.setdefault(label, []).append((e0, e1))
+
+    def prof_summary(self):
+        """mean milliseconds per op label (call after torch.cuda.synchronize())."""
+        out = {}
+        for k, evs in (self.prof or {}).items():
+            ts = [a.elapsed_time(b) for a, b in evs]
+            out[k] = dict(ms=sum(ts) / len(ts), calls=len(ts))
+        return out
 
     # ------------------------------------------------------------------------------------------
     def geometry(self, W, H, B, device) -> Geometry:
@@ -210,25 +236,25 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def _grid_conv(self, geom, lv, gs: GridState, xin, pack: _ConvPack, skip, out, st):
         level = geom.levels[lv]
-        _lib.check(self.lib.dagr_grid_conv(C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.mask),
+        self._run("grid_conv", self.lib.dagr_grid_conv, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.mask),
                                            _lib.ptr(xin), pack.cin, pack.cout, _lib.ptr(pack.weight), _lib.ptr(pack.rootT),
                                            _lib.ptr(pack.bias), _lib.ptr(pack.scale), _lib.ptr(pack.shift),
                                            _lib.ptr(skip), 1 if pack.relu else 0, level.den_x, level.den_y,
-                                           _lib.ptr(out), st), "grid_conv")
+                                           _lib.ptr(out), st)
 
     def _layer(self, geom, lv, gs: GridState, lp: _LayerPack, ws, name, st, dev):
         level = geom.levels[lv]
         cells = gs.cells
         cx = gs.x.shape[1]
         xin = self._buf(ws, name + "_in", (cells, cx + 2), torch.float32, dev)
-        _lib.check(self.lib.dagr_grid_cat_pos(C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.x), cx,
-                                              _lib.ptr(xin), st), "cat_pos")
+        self._run("cat_pos", self.lib.dagr_grid_cat_pos, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.x), cx,
+                                              _lib.ptr(xin), st)
         a = self._buf(ws, name + "_a", (cells, lp.a.cout), torch.float32, dev)
         self._grid_conv(geom, lv, gs, xin, lp.a, None, a, st)
         sk = self._buf(ws, name + "_s", (cells, lp.b.cout), torch.float32, dev)
-        _lib.check(self.lib.dagr_grid_linear_bn(cells, _lib.ptr(gs.cnt), _lib.ptr(xin), cx + 2, lp.b.cout,
+        self._run("linear_bn", self.lib.dagr_grid_linear_bn, cells, _lib.ptr(gs.cnt), _lib.ptr(xin), cx + 2, lp.b.cout,
                                                 _lib.ptr(lp.skipT), _lib.ptr(lp.sscale), _lib.ptr(lp.sshift),
-                                                _lib.ptr(sk), st), "linear_bn")
+                                                _lib.ptr(sk), st)
         out = self._buf(ws, name + "_o", (cells, lp.b.cout), torch.float32, dev)
         self._grid_conv(geom, lv, gs, a, lp.b, sk, out, st)
         return xin, a, out
@@ -247,21 +273,20 @@ class Engine:
         pcnt = self._zs(ws, f"pcnt{lp}", torch.int32)
         pmask = self._zs(ws, f"pmask{lp}", torch.int32)
         err = self._zs(ws, "err", torch.int32)
-        _lib.check(self.lib.dagr_grid_pool(C.byref(child.grid), C.byref(parent.grid), _lib.ptr(parent.cellx_dev),
+        self._run("grid_pool", self.lib.dagr_grid_pool, C.byref(child.grid), C.byref(parent.grid), _lib.ptr(parent.cellx_dev),
                                            _lib.ptr(parent.celly_dev), _lib.ptr(gc.cnt), _lib.ptr(gc.pxy),
                                            _lib.ptr(gc.tmean), _lib.ptr(gc.tmax), _lib.ptr(gc.mask), _lib.ptr(x), Cc, aggr,
                                            _lib.ptr(accmax), _lib.ptr(accsum), _lib.ptr(possum), _lib.ptr(ptmax),
-                                           _lib.ptr(pcnt), _lib.ptr(pmask), _lib.ptr(err), st), "grid_pool")
+                                           _lib.ptr(pcnt), _lib.ptr(pmask), _lib.ptr(err), st)
         gp.x = self._buf(ws, f"gx{lp}", (gp.cells, Cc), torch.float32, dev)
-        _lib.check(self.lib.dagr_grid_pool_finalize(C.byref(parent.grid), Cc, aggr, _lib.ptr(accmax), _lib.ptr(accsum),
+        self._run("grid_pool_finalize", self.lib.dagr_grid_pool_finalize, C.byref(parent.grid), Cc, aggr, _lib.ptr(accmax), _lib.ptr(accsum),
                                                     _lib.ptr(possum), _lib.ptr(ptmax), _lib.ptr(pcnt), _lib.ptr(gp.pxy),
-                                                    _lib.ptr(gp.tmean), _lib.ptr(gp.tmax), _lib.ptr(gp.x), st),
-                   "grid_pool_finalize")
+                                                    _lib.ptr(gp.tmean), _lib.ptr(gp.tmax), _lib.ptr(gp.x), st)
         gp.cnt = pcnt[:gp.cells]
         gp.mask = pmask[:gp.cells]
         if keep_temporal:
-            _lib.check(self.lib.dagr_grid_temporal_filter(C.byref(parent.grid), _lib.ptr(gp.cnt), _lib.ptr(gp.tmax),
-                                                          _lib.ptr(gp.mask), st), "temporal_filter")
+            self._run("temporal_filter", self.lib.dagr_grid_temporal_filter, C.byref(parent.grid), _lib.ptr(gp.cnt), _lib.ptr(gp.tmax),
+                                                          _lib.ptr(gp.mask), st)
         return gp
 
     # ------------------------------------------------------------------------------------------
@@ -287,31 +312,31 @@ class Engine:
         cellmask = self._zs(ws, "cellmask", torch.int32)
         poolmax = self._zs(ws, "poolmax", torch.int32)
         # ---- event level ---------------------------------------------------------------------
-        _lib.check(lib.dagr_graph_sort(g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ws["key"]),
+        self._run("graph_sort", lib.dagr_graph_sort, g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ws["key"]),
                                        _lib.ptr(ws["tmp"]), _lib.ptr(ws["count"]), _lib.ptr(ws["blocksums"]),
                                        _lib.ptr(ws["start"]), _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                                       _lib.ptr(ws["feat_s"]), st), "graph_sort")
-        _lib.check(lib.dagr_graph_search(g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                                         _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(cellmask), st), "graph_search")
-        _lib.check(lib.dagr_l1_conv_a(g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(nbr), _lib.ptr(off),
-                                      _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(ws["xa"]), st), "l1_conv_a")
+                                       _lib.ptr(ws["feat_s"]), st)
+        self._run("graph_search", lib.dagr_graph_search, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
+                                         _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(cellmask), st)
+        self._run("l1_conv_a", lib.dagr_l1_conv_a, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(nbr), _lib.ptr(off),
+                                      _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(ws["xa"]), st)
         x1 = None
         if self.keep_node_features:
             if ws["x1"] is None or ws["x1"].shape[0] < ws["cap"]:
                 ws["x1"] = torch.empty((ws["cap"], 16), dtype=torch.float32, device=dev)
             x1 = ws["x1"]
-        _lib.check(lib.dagr_l1_conv_b_pool(g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]),
+        self._run("l1_conv_b_pool", lib.dagr_l1_conv_b_pool, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]),
                                            _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]),
-                                           _lib.ptr(x1), _lib.ptr(poolmax), st), "l1_conv_b_pool")
+                                           _lib.ptr(x1), _lib.ptr(poolmax), st)
         g1: GridState = ws["grids"][0]
         g1.x = self._buf(ws, "gx0", (g1.cells, 16), torch.float32, dev)
-        _lib.check(lib.dagr_pool1_finalize(g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(ws["ti"]),
+        self._run("pool1_finalize", lib.dagr_pool1_finalize, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(ws["ti"]),
                                            _lib.ptr(poolmax), 16, _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean),
-                                           _lib.ptr(g1.tmax), _lib.ptr(g1.x), st), "pool1_finalize")
+                                           _lib.ptr(g1.tmax), _lib.ptr(g1.x), st)
         g1.mask = cellmask[:g1.cells]
         if kto:
-            _lib.check(lib.dagr_grid_temporal_filter(C.byref(geom.levels[0].grid), _lib.ptr(g1.cnt), _lib.ptr(g1.tmax),
-                                                     _lib.ptr(g1.mask), st), "temporal_filter")
+            self._run("temporal_filter", lib.dagr_grid_temporal_filter, C.byref(geom.levels[0].grid), _lib.ptr(g1.cnt), _lib.ptr(g1.tmax),
+                                                     _lib.ptr(g1.mask), st)
         # ---- coarse levels -------------------------------------------------------------------
         aggr_cfg = 0 if getattr(model.args, "pooling_aggr", "max") == "max" else 1
         lay = pk["layers"]
@@ -350,12 +375,12 @@ class Engine:
                 add = None
                 if image_outs is not None:
                     add = image_outs[name + "_output"][k].float().contiguous()
-                _lib.check(lib.dagr_grid_to_dense(C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(o), cpk.cout,
-                                                  _lib.ptr(add), _lib.ptr(d), st), "to_dense")
+                self._run("to_dense", lib.dagr_grid_to_dense, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(o), cpk.cout,
+                                                  _lib.ptr(add), _lib.ptr(d), st)
                 dense[name] = d
             stride = model.backbone.strides[k]
-            _lib.check(lib.dagr_head_decode(_lib.ptr(dense["reg"]), _lib.ptr(dense["obj"]), _lib.ptr(dense["cls"]), B, nc,
-                                            level.ny, level.nx, int(stride), a0, A, _lib.ptr(out), st), "head_decode")
+            self._run("head_decode", lib.dagr_head_decode, _lib.ptr(dense["reg"]), _lib.ptr(dense["obj"]), _lib.ptr(dense["cls"]), B, nc,
+                                            level.ny, level.nx, int(stride), a0, A, _lib.ptr(out), st)
             a0 += level.nx * level.ny
             dense_all.append(dense)
         self.last = dict(geom=geom, ws=ws, N=N, grids=[g1, g2, g3, g4], inter=inter, dense=dense_all, x1=x1)
@@ -369,9 +394,9 @@ class Engine:
         dev = decoded.device
         det = torch.empty((B, A, 6), dtype=torch.float32, device=dev)
         ndet = torch.empty(B, dtype=torch.int32, device=dev)
-        _lib.check(self.lib.dagr_postprocess_nms(_lib.ptr(decoded), B, A, nc, float(conf_thre), float(nms_thre), int(width),
+        self._run("postprocess_nms", self.lib.dagr_postprocess_nms, _lib.ptr(decoded), B, A, nc, float(conf_thre), float(nms_thre), int(width),
                                                  int(height), 1 if filtering else 0, _lib.ptr(det), _lib.ptr(ndet),
-                                                 _lib.stream_ptr()), "postprocess_nms")
+                                                 _lib.stream_ptr())
         return det, ndet
 
     # ------------------------------------------------------------------------------------------
@@ -388,8 +413,8 @@ class Engine:
         rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
         es = torch.empty(cap, dtype=torch.int64, device=dev)
         ed = torch.empty(cap, dtype=torch.int64, device=dev)
-        _lib.check(self.lib.dagr_graph_export(C.byref(geom.c_geom), N, _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]),
+        self._run("graph_export", self.lib.dagr_graph_export, C.byref(geom.c_geom), N, _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]),
                                               _lib.ptr(ws["nbr"]), _lib.ptr(inv), _lib.ptr(rowptr), _lib.ptr(ws["blocksums"]),
-                                              _lib.ptr(es), _lib.ptr(ed), cap, _lib.stream_ptr()), "graph_export")
+                                              _lib.ptr(es), _lib.ptr(ed), cap, _lib.stream_ptr())
         E = int(rowptr[N].item())
         return torch.stack([es[:E], ed[:E]])

@@ -207,6 +207,9 @@ def message_lut(x_j, edge_attr, lut, remap):
     return torch.einsum("nio,ni->no", w, x_j)
 
 
+CHUNK_ELEMS = 64_000_000     # floats per [E,Cin,Cout] temporary
+
+
 def to_sparse(edge_index: torch.Tensor, edge_attr: torch.Tensor, N: int):
     """PyG ToSparseTensor: stable sort of edges (and attrs) by key dst*N + src; CSR over dst."""
     row, col = edge_index
@@ -228,13 +231,19 @@ def spline_conv(x: torch.Tensor, edge_index: torch.Tensor, edge_attr: torch.Tens
     if edge_index.numel() > 0:                                      # spline_conv.py:67-70
         attr = edge_attr[:, :2]
         src, dst, attr = to_sparse(edge_index, attr, N)
-        x_j = x[src]
-        if lut is not None:
-            msg = message_lut(x_j, attr, lut, remap)
-        else:
-            basis, index = spline_basis(attr, kernel_size, True, 1)
-            msg = spline_weighting(x_j, weight, basis, index)
-        out.index_add_(0, dst, msg)
+        E = src.shape[0]
+        # edges are processed in chunks only to bound the [E,Cin,Cout] temporary (the reference
+        # materialises it in one go, spline_conv.py:44); per-destination order is unchanged
+        step = max(1, int(CHUNK_ELEMS // max(1, weight.shape[1] * weight.shape[2])))
+        for s0 in range(0, E, step):
+            sl = slice(s0, min(E, s0 + step))
+            x_j = x[src[sl]]
+            if lut is not None:
+                msg = message_lut(x_j, attr[sl], lut, remap)
+            else:
+                basis, index = spline_basis(attr[sl], kernel_size, True, 1)
+                msg = spline_weighting(x_j, weight, basis, index)
+            out.index_add_(0, dst[sl], msg)
     out = out + x @ root.t()                                        # :72-73
     if bias is not None:
         out = out + bias                                            # :75-76
