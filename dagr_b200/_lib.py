@@ -32,7 +32,7 @@ class Geom(C.Structure):
                 ("nx1", i32), ("ny1", i32),
                 ("CW", i32), ("CH", i32), ("CP", i32),
                 ("NK", i32),
-                ("xkey", p), ("ykey", p), ("spiral", p), ("posx0", p), ("posy0", p)]
+                ("xkey", p), ("ykey", p), ("spiral", p), ("posx0", p), ("posy0", p), ("vx0", p), ("vy0", p)]
 
 
 class Grid(C.Structure):
@@ -56,8 +56,9 @@ _SIGS = {
     "dagr_last_error": (C.c_char_p, []),
     "dagr_scan_blocks": (i64, [i64]),
     "dagr_denormalize_pos": (C.c_int, [p, i64, C.c_int, C.c_int, C.c_int, p, p]),
-    "dagr_graph_sort": (C.c_int, [C.POINTER(Geom), p, p, p, i64, p, p, p, p, p, p, p, p, p, p]),
+    "dagr_graph_sort": (C.c_int, [C.POINTER(Geom), p, p, p, i64, p, p, p, p, p, p, p, p, p, p, p]),
     "dagr_graph_search": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, p]),
+    "dagr_l1_build": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, C.POINTER(L1AParams), p, p, p, p, p, p]),
     "dagr_graph_export": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, p, p, i64, p]),
     "dagr_l1_conv_a": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, C.POINTER(L1AParams), p, p]),
     "dagr_l1_conv_b_pool": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, C.POINTER(L1BParams), p, p, p]),

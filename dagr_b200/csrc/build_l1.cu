@@ -1,0 +1,415 @@
+// build_l1.cu -- fused event-level build: spiral probe on a shared-memory hashed grid + conv_a.
+//
+// One CTA per pool1 voxel.  Because events are stored in cell-major order, the voxel's own events are
+// one contiguous range and the events of its 3x3 voxel neighbourhood are THREE contiguous runs (one per
+// voxel row), so the (t, arrival idx, polarity) records the probe needs are staged in shared memory
+// with fully coalesced loads.  A per-tile-pixel bin table (shared memory) maps each of the
+// (CW+2r) x (CH+2r) pixels the voxel's events can reach to its FIFO column (newest <= Q entries,
+// ev_graph.cu:201-211).  The spiral probe (ev_graph.cu:49-78) then runs entirely on chip; accepted
+// neighbours are written to the column-major ELL and folded into conv_block1.conv_block1 on the fly
+// (their features are (polarity, x/W, y/H): no gather at all).
+// Voxels whose neighbourhood does not fit the staging buffer fall back to probing global memory.
+#include "common.cuh"
+
+#define BL_THREADS 192           // >= events of a voxel at the nominal density (Poisson mean 134): one pass
+#define BL_CAP 2560              // staged neighbourhood records per CTA (uniform 300k events/sample: ~1200)
+#define BL_NB 8                  // time buckets of width delta_t kept per tile pixel
+
+struct BLTile {
+    int X0, Y0, TW, TH;          // tile origin (pixel) and extent
+    int run_start[3], run_off[3], run_len[3];
+    int smin, smax;              // slice (t / delta_t) range of the voxel's own events
+    int unsorted;                // some pixel's records are not time-sorted -> no time bucketing
+};
+
+#define BL_R1 96                 // spiral cells walked one-thread-per-event before unsaturated events are handed
+                                 // to the warp-cooperative continuation (saturated events need ~85 cells)
+
+// Phase 1: warp-converged probe.  All lanes walk the spiral in lock step (same cell index c), four cells per
+// iteration so the dependent shared-memory loads pipeline; the per-bin record loop runs to the warp-wide
+// maximum with predication and the walk ends when every lane has its K-1 neighbours.  Lanes of a warp are
+// events of similar age (threads are assigned in arrival order) and each tile pixel exposes only the
+// sub-range of its FIFO column that can lie within delta_t of the event (time buckets), so the common
+// iteration touches no record at all.
+template <bool STAGED>
+__device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p, bool active, const int2 me, int eb, int tidx0,
+                                         int c_end, const uint32_t *s_pbin, const uint16_t *s_rng, const short *s_sp2,
+                                         const int2 *s_ti, const int2 *__restrict__ ti,
+                                         int32_t *__restrict__ nbr, uint16_t *__restrict__ off, int &n_out)
+{
+    const int kmax = g.K - 1;
+    int n = active ? 0 : kmax;
+    for (int c0 = 0; c0 < c_end; c0 += 4) {
+        if (__all_sync(0xffffffffu, n >= kmax)) break;
+        uint32_t rg[4]; int pix[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int c = min(c0 + u, g.ncell - 1);
+            pix[u] = tidx0 + s_sp2[c];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) rg[u] = s_rng[pix[u] * BL_NB + eb];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int c = c0 + u;
+            const int lo = rg[u] & 0xff, hi = rg[u] >> 8;
+            const int cnt = (c < c_end && n < kmax) ? hi - lo : 0;
+            if (!__any_sync(0xffffffffu, cnt > 0)) continue;
+            const int base = (int)(s_pbin[pix[u]] >> 8);
+            const int vmax = __reduce_max_sync(0xffffffffu, cnt);
+            for (int k = 0; k < vmax; k++) {
+                if (k < cnt && n < kmax) {
+                    // FIFO order: newest first.  Visible records of the pixel are [base, base+vis) in arrival order;
+                    // the bucket range [lo,hi) counts from the OLDEST visible record.
+                    const int j = base + hi - 1 - k;
+                    const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
+                    if (o.y < me.y && me.x - o.x <= g.dt_us) {              // ev_graph.cu:64-69
+                        nbr[(int64_t)n * N + p] = j;                        // staged index for now; fixed up in phase B
+                        off[(int64_t)n * N + p] = (uint16_t)c;
+                        n++;
+                    }
+                }
+            }
+        }
+    }
+    n_out = active ? n : 0;
+}
+
+// Phase 2: warp-cooperative continuation for one unsaturated event: the 32 lanes test 32 consecutive spiral
+// cells at once; an exclusive scan over the lanes' accept counts restores the spiral order and the K cap.
+template <bool STAGED>
+__device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, int p, const int2 me, int eb, int tidx0, int c_begin,
+                                             int n, const uint32_t *s_pbin, const uint16_t *s_rng, const short *s_sp2,
+                                             const int2 *s_ti, const int2 *__restrict__ ti,
+                                             int32_t *__restrict__ nbr, uint16_t *__restrict__ off)
+{
+    const int kmax = g.K - 1;
+    const int lane = threadIdx.x & 31;
+    for (int c0 = c_begin; c0 < g.ncell && n < kmax; c0 += 32) {
+        const int c = c0 + lane;
+        int cnt = 0, base = 0, hi = 0, acc = 0;
+        if (c < g.ncell) {
+            const int pix = tidx0 + s_sp2[c];
+            const uint32_t rg = s_rng[pix * BL_NB + eb];
+            hi = rg >> 8; cnt = hi - (int)(rg & 0xff);
+            base = (int)(s_pbin[pix] >> 8);
+            for (int k = 0; k < cnt; k++) {
+                const int2 o = STAGED ? s_ti[base + hi - 1 - k] : __ldg(ti + base + hi - 1 - k);
+                acc += (o.y < me.y && me.x - o.x <= g.dt_us) ? 1 : 0;
+            }
+        }
+        int incl = acc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (acc > 0) {
+            int slot = n + incl - acc;
+            for (int k = 0; k < cnt && slot < kmax; k++) {
+                const int j = base + hi - 1 - k;
+                const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
+                if (o.y < me.y && me.x - o.x <= g.dt_us) {
+                    nbr[(int64_t)slot * N + p] = j;
+                    off[(int64_t)slot * N + p] = (uint16_t)c;
+                    slot++;
+                }
+            }
+        }
+        n = min(n + tot, kmax);
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(BL_THREADS)
+k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const int2 *__restrict__ ti,
+           const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
+           const __grid_constant__ dagr_l1a_params_t P, const int32_t *__restrict__ flags, int32_t *__restrict__ nbr,
+           uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask, float *__restrict__ xa)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ BLTile T;
+    __shared__ uint32_t s_mask;
+    __shared__ int s_ntodo;
+    __shared__ int4 s_ev[BL_THREADS];
+    __shared__ int s_evn[BL_THREADS];
+    __shared__ uint16_t s_todo[BL_THREADS];
+    const int cell = blockIdx.x;
+    const int per = g.ny1 * g.nx1;
+    const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
+    const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
+    if (p1 == p0) { if (threadIdx.x == 0) cellmask[cell] = 0; return; }      // block-uniform
+
+    // ---- shared memory carve-up -------------------------------------------------------------------
+    const int TWmax = g.CW + 2 * g.r, THmax = g.CH + 2 * g.r, TPmax = TWmax * THmax;
+    int2 *s_ti = (int2 *)smem_raw;                                      // [BL_CAP]
+    float *s_feat = (float *)(s_ti + BL_CAP);                           // [BL_CAP]
+    uint32_t *s_pbin = (uint32_t *)(s_feat + BL_CAP);                   // [TP]  pos << 8 | visible count
+    float *s_posx = (float *)(s_pbin + TPmax);                          // [TWmax]
+    float *s_posy = s_posx + TWmax;                                     // [THmax]
+    uint16_t *s_rng = (uint16_t *)(s_posy + THmax);                     // [TP][BL_NB]  lo | hi << 8
+    short *s_sp = (short *)(s_rng + TPmax * BL_NB);                     // [ncell]  dx | dy << 8
+    short *s_sp2 = s_sp + g.ncell;                                      // [ncell]  dy*TW + dx
+    uint16_t *s_order = (uint16_t *)(s_sp2 + g.ncell);                  // [BL_THREADS]
+    unsigned char *s_colv = (unsigned char *)(s_order + BL_THREADS);    // [TWmax]
+    unsigned char *s_rowv = s_colv + TWmax;                             // [THmax]
+
+    const int dtw = max(g.dt_us, 1);
+    if (threadIdx.x == 0) {
+        const int X0 = g.vx0[cx], X1 = g.vx0[cx + 1], Y0 = g.vy0[cy], Y1 = g.vy0[cy + 1];
+        T.X0 = X0 - g.r; T.Y0 = Y0 - g.r; T.TW = X1 - X0 + 2 * g.r; T.TH = Y1 - Y0 + 2 * g.r;
+        const int clo = max(cx - 1, 0), chi = min(cx + 1, g.nx1 - 1);
+        int o = 0;
+        for (int rr = 0; rr < 3; rr++) {
+            const int ry = cy - 1 + rr;
+            if (ry < 0 || ry >= g.ny1) { T.run_start[rr] = 0; T.run_len[rr] = 0; T.run_off[rr] = o; continue; }
+            const int64_t c0 = (int64_t)b * per + ry * g.nx1 + clo, c1 = (int64_t)b * per + ry * g.nx1 + chi + 1;
+            const int s = start[c0 * g.CP], e = start[c1 * g.CP];
+            T.run_start[rr] = s; T.run_len[rr] = e - s; T.run_off[rr] = o;
+            o += e - s;
+        }
+        T.smin = 0x7fffffff; T.smax = -0x7fffffff; T.unsorted = 0;
+        s_mask = 0;
+    }
+    __syncthreads();
+    const int TW = T.TW, TH = T.TH, TP = TW * TH;
+    const int total = T.run_off[2] + T.run_len[2];
+    const bool staged = total <= BL_CAP;                                // block-uniform
+    const int bbase = b * per * g.CP;
+
+    for (int i = threadIdx.x; i < g.ncell; i += blockDim.x) {
+        const int dx = g.spiral[2 * i], dy = g.spiral[2 * i + 1];
+        s_sp[i] = (short)((dx & 0xff) | (dy << 8));
+        s_sp2[i] = (short)(dy * TW + dx);
+    }
+    // ---- tile tables: per-pixel FIFO bin, normalised positions, voxel direction ---------------------
+    for (int i = threadIdx.x; i < TW; i += blockDim.x) {
+        const int gx = T.X0 + i;
+        const bool in = gx >= 0 && gx < g.W;
+        s_posx[i] = in ? g.posx0[gx] : 0.f;
+        s_colv[i] = (unsigned char)(in ? (g.xkey[gx] / g.CP - cx + 1) : 1);
+    }
+    for (int i = threadIdx.x; i < TH; i += blockDim.x) {
+        const int gy = T.Y0 + i;
+        const bool in = gy >= 0 && gy < g.H;
+        s_posy[i] = in ? g.posy0[gy] : 0.f;
+        s_rowv[i] = (unsigned char)(in ? (g.ykey[gy] / (g.nx1 * g.CP) - cy + 1) : 1);
+    }
+    for (int i = threadIdx.x; i < TP; i += blockDim.x) {
+        const int ty = i / TW, tx = i % TW;
+        const int gx = T.X0 + tx, gy = T.Y0 + ty;
+        uint32_t v = 0;
+        if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H) {
+            const int ky = g.ykey[gy], kx = g.xkey[gx];
+            const int k = bbase + ky + kx;
+            const int s = start[k], e = start[k + 1];
+            if (e > s) {
+                const int lo = max(s, e - g.Q);                         // newest Q entries (ev_graph.cu:201-211)
+                const int rr = ky / (g.nx1 * g.CP) - cy + 1;
+                const int pos = staged ? (lo - T.run_start[rr] + T.run_off[rr]) : lo;
+                v = ((uint32_t)pos << 8) | (uint32_t)(e - lo);
+            }
+        }
+        s_pbin[i] = v;
+    }
+    // ---- stage the neighbourhood records (three coalesced runs) -------------------------------------
+    if (staged) {
+        for (int rr = 0; rr < 3; rr++) {
+            const int s = T.run_start[rr], o = T.run_off[rr], len = T.run_len[rr];
+            for (int i = threadIdx.x; i < len; i += blockDim.x) {
+                s_ti[o + i] = ti[s + i];
+                s_feat[o + i] = feat_s[s + i];
+            }
+        }
+    }
+    // slice range of the voxel's own events
+    {
+        int mn = 0x7fffffff, mx = -0x7fffffff;
+        for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) { const int sl = ti[p].x / dtw; mn = min(mn, sl); mx = max(mx, sl); }
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&T.smin, mn); atomicMax(&T.smax, mx); }
+    }
+    __syncthreads();
+    // ---- per-pixel time-bucket ranges ---------------------------------------------------------------
+    // bucket(t) = clamp(t/delta_t - (smin-1), 0, NB-1); an event in bucket e needs records of buckets {e-1, e}.
+    const int sbase = T.smin - 1;
+    bool bucketed = staged && (T.smax - sbase) < BL_NB && (flags == nullptr || flags[0] == 0);   // block-uniform
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = threadIdx.x; i < TP; i += blockDim.x) {
+            const uint32_t pb = s_pbin[i];
+            const int vis = pb & 0xff, base = pb >> 8;
+            unsigned char cum[BL_NB + 1];
+#pragma unroll
+            for (int q = 0; q <= BL_NB; q++) cum[q] = 0;
+            if (bucketed) {
+                int prev = 0;
+                for (int k = 0; k < vis; k++) {
+                    int bk = s_ti[base + k].x / dtw - sbase;
+                    bk = min(max(bk, 0), BL_NB - 1);
+                    if (bk < prev) T.unsorted = 1;                      // benign race: any writer sets 1
+                    prev = bk;
+#pragma unroll
+                    for (int q = 0; q <= BL_NB; q++) cum[q] += (bk < q) ? 1 : 0;
+                }
+            } else {
+#pragma unroll
+                for (int q = 1; q <= BL_NB; q++) cum[q] = (unsigned char)vis;
+            }
+#pragma unroll
+            for (int e = 0; e < BL_NB; e++) {
+                const int lo = cum[e > 0 ? e - 1 : 0], hi = cum[e + 1];
+                s_rng[i * BL_NB + e] = (uint16_t)(lo | (hi << 8));
+            }
+        }
+        __syncthreads();
+        if (!bucketed || !T.unsorted) break;                            // block-uniform
+        bucketed = false;                                               // records not time-sorted: redo without buckets
+    }
+    // ---- thread <-> event assignment in arrival order (time-homogeneous warps) ------------------------
+    const int nown = p1 - p0;
+    const int own_off = staged ? (p0 - T.run_start[1] + T.run_off[1]) : 0;
+    uint32_t mloc = 0;
+    for (int pb0 = 0; pb0 < nown; pb0 += blockDim.x) {
+        const int chunk = min((int)blockDim.x, nown - pb0);
+        __syncthreads();
+        // rank of each event of the chunk by arrival index
+        if ((int)threadIdx.x < chunk) {
+            const int myidx = staged ? s_ti[own_off + pb0 + threadIdx.x].y : ti[p0 + pb0 + threadIdx.x].y;
+            int rank = 0;
+            for (int k = 0; k < chunk; k++) {
+                const int oi = staged ? s_ti[own_off + pb0 + k].y : __ldg(&ti[p0 + pb0 + k].y);
+                rank += (oi < myidx) ? 1 : 0;
+            }
+            s_order[rank] = (uint16_t)threadIdx.x;
+        }
+        __syncthreads();
+        const bool active = (int)threadIdx.x < chunk;
+        const int p = p0 + pb0 + (active ? (int)s_order[threadIdx.x] : 0);
+        int x = 0, y = 0;
+        int2 me = make_int2(0, 0);
+        if (active) {
+            const uint32_t w = xyb[p];
+            x = w & 0xfff; y = (w >> 12) & 0xfff;
+            me = ti[p];
+        }
+        const int tx0 = active ? x - T.X0 : g.r, ty0 = active ? y - T.Y0 : g.r;
+        int eb = 0;
+        if (bucketed) eb = min(max(me.x / dtw - sbase, 0), BL_NB - 1);
+        int n;
+        const int tidx0 = ty0 * TW + tx0;
+        if (staged) bl_probe<true>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, nbr, off, n);
+        else        bl_probe<false>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, nbr, off, n);
+        // hand events that are still unsaturated after BL_R1 cells to the warp-cooperative continuation
+        if (BL_R1 < g.ncell) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_ntodo = 0;
+            __syncthreads();
+            s_evn[threadIdx.x] = n;
+            if (active && n < g.K - 1) {
+                s_ev[threadIdx.x] = make_int4(p, me.x, me.y, (eb << 16) | tidx0);
+                s_todo[atomicAdd(&s_ntodo, 1)] = (uint16_t)threadIdx.x;
+            }
+            __syncthreads();
+            const int ntodo = s_ntodo;
+            for (int i = threadIdx.x >> 5; i < ntodo; i += (blockDim.x >> 5)) {
+                const int who = s_todo[i];
+                const int4 ev = s_ev[who];
+                const int nn = staged ? bl_probe_coop<true>(g, N, ev.x, make_int2(ev.y, ev.z), ev.w >> 16, ev.w & 0xffff, BL_R1, s_evn[who],
+                                                            s_pbin, s_rng, s_sp2, s_ti, ti, nbr, off)
+                                      : bl_probe_coop<false>(g, N, ev.x, make_int2(ev.y, ev.z), ev.w >> 16, ev.w & 0xffff, BL_R1, s_evn[who],
+                                                             s_pbin, s_rng, s_sp2, s_ti, ti, nbr, off);
+                if ((threadIdx.x & 31) == 0) s_evn[who] = nn;
+            }
+            __syncthreads();
+            n = s_evn[threadIdx.x];
+        }
+        if (active) nbr[(int64_t)(DAGR_ELL - 1) * N + p] = n;
+        // phase B: A_u = sum_e tab[c_e][u] * (polarity_src, x_src/W, y_src/H), converged over the ELL slots;
+        // also translates the staged record index into the global sorted position and collects the voxel mask
+        const float f0 = active ? feat_s[p] : 0.f, f1 = s_posx[tx0], f2 = s_posy[ty0];
+        float A[DAGR_KU][3];
+        {
+#pragma unroll
+            for (int u = 0; u < DAGR_KU; u++) { const float t = __ldg(tab + u); A[u][0] = t * f0; A[u][1] = t * f1; A[u][2] = t * f2; }
+        }
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        for (int q = 0; q < nmax; q++) {
+            if (q < n) {
+                const int j = nbr[(int64_t)q * N + p];
+                const int c = off[(int64_t)q * N + p];
+                const int sp = s_sp[c];
+                const int tx = tx0 + (int)(signed char)(sp & 0xff), ty = ty0 + (sp >> 8);
+                const int rr = s_rowv[ty];
+                float e0;
+                if (staged) {
+                    e0 = s_feat[j];
+                    nbr[(int64_t)q * N + p] = j - T.run_off[rr] + T.run_start[rr];
+                } else e0 = __ldg(feat_s + j);
+                const int dcx = (int)s_colv[tx] - 1, dcy = rr - 1;
+                if (dcx | dcy) mloc |= 1u << ((dcy + 1) * 3 + (dcx + 1));
+                const float e1 = s_posx[tx], e2 = s_posy[ty];
+                const float4 *tr = reinterpret_cast<const float4 *>(tab + c * DAGR_TABW);
+                const float4 t0 = __ldg(tr), t1 = __ldg(tr + 1), t2 = __ldg(tr + 2), t3 = __ldg(tr + 3);
+                const float t[DAGR_KU] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z};
+#pragma unroll
+                for (int u = 0; u < DAGR_KU; u++) {
+                    A[u][0] = fmaf(t[u], e0, A[u][0]);
+                    A[u][1] = fmaf(t[u], e1, A[u][1]);
+                    A[u][2] = fmaf(t[u], e2, A[u][2]);
+                }
+            }
+        }
+        if (!active) continue;
+        // conv_a phase 2: out = sum_u W_u^T A_u + W_root^T x_i, BN, act  (weights in the constant bank)
+        float o[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) o[k] = 0.f;
+#pragma unroll
+        for (int u = 0; u < DAGR_KU; u++)
+#pragma unroll
+            for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+                for (int k = 0; k < 16; k++) o[k] = fmaf(A[u][ci], P.w[u][ci][k], o[k]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            float r = o[k];
+            r = fmaf(f0, P.root[0][k], r);
+            r = fmaf(f1, P.root[1][k], r);
+            r = fmaf(f2, P.root[2][k], r);
+            r = fmaf(r, P.scale[k], P.shift[k]);
+            o[k] = P.relu ? fmaxf(r, 0.f) : r;
+        }
+        float4 *dst = reinterpret_cast<float4 *>(xa + (int64_t)p * 16);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+        dst[3] = make_float4(o[12], o[13], o[14], o[15]);
+    }
+    mloc = __reduce_or_sync(0xffffffffu, mloc);
+    if ((threadIdx.x & 31) == 0 && mloc) atomicOr(&s_mask, mloc);
+    __syncthreads();
+    if (threadIdx.x == 0) cellmask[cell] = s_mask;
+}
+
+static size_t bl_smem_bytes(const dagr_geom_t *g)
+{
+    const size_t TW = g->CW + 2 * g->r, TH = g->CH + 2 * g->r, TP = TW * TH;
+    return (size_t)BL_CAP * 12 + TP * 4 + (TW + TH) * 4 + TP * BL_NB * 2 + (size_t)g->ncell * 4 + BL_THREADS * 2 + (TW + TH) + 64;
+}
+
+extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
+                             const uint32_t *xyb, const float *feat_s, const float *tab,
+                             const dagr_l1a_params_t *p_host, const int32_t *flags, int32_t *nbr, uint16_t *off,
+                             uint32_t *cellmask, float *xa, void *stream)
+{
+    DAGR_CHECK_ARG(g && p_host, "null argument");
+    DAGR_CHECK_ARG(g->K >= 1 && g->K <= DAGR_ELL, "max_neighbors must be in [1,16]");
+    DAGR_CHECK_ARG(g->r >= 0 && g->r <= 15 && g->Q <= 255, "radius must be <= 15 px and max_queue_size <= 255");
+    DAGR_CHECK_ARG(N < (1ll << 24), "the staged probe packs positions in 24 bits (N < 16.7M per call)");
+    const int cells = g->B * g->ny1 * g->nx1;
+    const size_t smem = bl_smem_bytes(g);
+    DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    k_l1_build<<<cells, BL_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab, *p_host,
+                                                                  flags, nbr, off, cellmask, xa);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}

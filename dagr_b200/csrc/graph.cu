@@ -131,11 +131,14 @@ extern "C" int dagr_denormalize_pos(const float *pos, int64_t N, int W, int H, i
 // sort
 // ------------------------------------------------------------------------------------------------
 __global__ void k_keys_hist(dagr_geom_t g, const int32_t *__restrict__ batch, const int32_t *__restrict__ pos, int64_t N,
-                            int32_t *__restrict__ key, int32_t *__restrict__ count)
+                            int32_t *__restrict__ key, int32_t *__restrict__ count, int32_t *__restrict__ flags)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int x = pos[3 * i], y = pos[3 * i + 1], b = batch[i];
+    // contract check: events are time-sorted within each sample.  If not, flags[0] = 1 and the
+    // build kernel disables its time-bucket pruning (results stay exact, only slower).
+    if (flags != nullptr && i > 0 && batch[i - 1] == b && pos[3 * (i - 1) + 2] > pos[3 * i + 2]) flags[0] = 1;
     // out-of-range events are clamped into the grid (the reference would index out of bounds)
     x = min(max(x, 0), g.W - 1); y = min(max(y, 0), g.H - 1); b = min(max(b, 0), g.B - 1);
     int k = b * (g.ny1 * g.nx1 * g.CP) + __ldg(g.ykey + y) + __ldg(g.xkey + x);
@@ -179,13 +182,13 @@ __global__ void k_rank_emit(dagr_geom_t g, const int32_t *__restrict__ key, cons
 extern "C" int dagr_graph_sort(const dagr_geom_t *g, const int32_t *batch, const int32_t *pos, const float *feat,
                                int64_t N, int32_t *key, int32_t *tmp, int32_t *count, int32_t *blocksums,
                                int32_t *start, int32_t *perm, int32_t *ti, uint32_t *xyb, float *feat_s,
-                               void *stream)
+                               int32_t *flags, void *stream)
 {
     DAGR_CHECK_ARG(g && g->W <= 4096 && g->H <= 4096 && g->B <= 256, "geometry out of range (W,H<=4096, B<=256)");
     DAGR_CHECK_ARG(N >= 0 && N < (1ll << 31), "N out of range");
     cudaStream_t st = (cudaStream_t)stream;
     if (N > 0) {
-        k_keys_hist<<<dagr_div_up(N, 256), 256, 0, st>>>(*g, batch, pos, N, key, count);
+        k_keys_hist<<<dagr_div_up(N, 256), 256, 0, st>>>(*g, batch, pos, N, key, count, flags);
         DAGR_CHECK_LAUNCH();
     }
     scan_exclusive(count, start, g->NK, blocksums, st);      // start[NK] = N

@@ -76,12 +76,13 @@ class Engine:
         self._pack_key = None
         self._ws: Dict[tuple, dict] = {}
         self.keep_node_features = False      # debug / parity: materialise per-event activations
+        self.fused_build = True              # probe + conv_a in one shared-memory-tiled kernel (False: v1 split kernels)
         self.last = {}
         self.launches = 0                    # kernels of libdagr_b200.so enqueued so far
         self.prof = None                     # dict name -> [(start_evt, end_evt)] when per-op timing is on
 
     # kernels enqueued by each C-ABI call (see csrc/*.cu)
-    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1,
+    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1,
                      dagr_pool1_finalize=1, dagr_grid_cat_pos=1, dagr_grid_conv=1, dagr_grid_linear_bn=1, dagr_grid_pool=1,
                      dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1,
                      dagr_postprocess_nms=1, dagr_sample_features=1, dagr_denormalize_pos=1)
@@ -209,6 +210,7 @@ class Engine:
                 take(f"pcnt{lv}", cells * 4)
                 take(f"pmask{lv}", cells * 4)
             take("err", 4)
+            take("flags", 16)
             ws["zero_buf"] = torch.zeros(off, dtype=torch.uint8, device=dev)
             ws["zero_slices"] = sizes
             grids = []
@@ -311,15 +313,21 @@ class Engine:
         nbr, off = ws["nbr"], ws["off"]
         cellmask = self._zs(ws, "cellmask", torch.int32)
         poolmax = self._zs(ws, "poolmax", torch.int32)
+        flags = self._zs(ws, "flags", torch.int32)
         # ---- event level ---------------------------------------------------------------------
         self._run("graph_sort", lib.dagr_graph_sort, g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ws["key"]),
                                        _lib.ptr(ws["tmp"]), _lib.ptr(ws["count"]), _lib.ptr(ws["blocksums"]),
                                        _lib.ptr(ws["start"]), _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                                       _lib.ptr(ws["feat_s"]), st)
-        self._run("graph_search", lib.dagr_graph_search, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                                         _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(cellmask), st)
-        self._run("l1_conv_a", lib.dagr_l1_conv_a, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(nbr), _lib.ptr(off),
-                                      _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(ws["xa"]), st)
+                                       _lib.ptr(ws["feat_s"]), _lib.ptr(flags), st)
+        if self.fused_build:
+            self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
+                      _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(flags), _lib.ptr(nbr), _lib.ptr(off),
+                      _lib.ptr(cellmask), _lib.ptr(ws["xa"]), st)
+        else:
+            self._run("graph_search", lib.dagr_graph_search, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
+                                             _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(cellmask), st)
+            self._run("l1_conv_a", lib.dagr_l1_conv_a, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(nbr), _lib.ptr(off),
+                                          _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(ws["xa"]), st)
         x1 = None
         if self.keep_node_features:
             if ws["x1"] is None or ws["x1"].shape[0] < ws["cap"]:

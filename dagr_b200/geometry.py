@@ -162,6 +162,10 @@ class Geometry:
         if self.r >= min(minw, minh):
             raise ValueError(f"event radius {self.r}px must be smaller than a pool1 voxel ({minw}x{minh}px): "
                              "coarse edges would span more than the 8-neighbourhood")
+        self.vx0 = torch.cat([x0, torch.tensor([W])]).int()
+        self.vy0 = torch.cat([y0, torch.tensor([H])]).int()
+        if int(cx.max()) + 1 != self.nx1 or int(cy.max()) + 1 != self.ny1:
+            raise ValueError("empty voxel columns/rows in the pool1 grid")
         self.xkey = (cx * self.CP + (torch.arange(W) - x0[cx])).int()
         self.ykey = (cy * self.nx1 * self.CP + (torch.arange(H) - y0[cy]) * self.CW).int()
         self.NK = B * self.ny1 * self.nx1 * self.CP
@@ -201,6 +205,8 @@ class Geometry:
         self.d_posxr = self.posxr.to(dev)
         self.d_posyr = self.posyr.to(dev)
         self.d_tab1 = self.tab1.to(dev)
+        self.d_vx0 = self.vx0.to(dev)
+        self.d_vy0 = self.vy0.to(dev)
         g = _lib.Geom()
         g.W, g.H, g.B, g.T = self.W, self.H, self.B, self.T
         g.r, g.ncell = self.r, self.ncell
@@ -211,6 +217,7 @@ class Geometry:
         g.xkey = self.d_xkey.data_ptr(); g.ykey = self.d_ykey.data_ptr()
         g.spiral = self.d_spiral.data_ptr()
         g.posx0 = self.d_posx0.data_ptr(); g.posy0 = self.d_posy0.data_ptr()
+        g.vx0 = self.d_vx0.data_ptr(); g.vy0 = self.d_vy0.data_ptr()
         self.c_geom = g
         for lv in self.levels:
             gr = _lib.Grid()

@@ -50,6 +50,8 @@ typedef struct {
     const int8_t  *spiral;         /* [ncell][2] spiral probe order (spiral.h:1-16)                  */
     const float   *posx0;          /* [W]  fl(x / W)  (buffers.py:43)                                */
     const float   *posy0;          /* [H]  fl(y / H)                                                 */
+    const int32_t *vx0;            /* [nx1+1] first pixel column of each pool1 voxel (vx0[nx1] = W)  */
+    const int32_t *vy0;            /* [ny1+1] first pixel row of each pool1 voxel    (vy0[ny1] = H)  */
 } dagr_geom_t;
 
 /* ---------------------------------------------------------------------------------------------
@@ -84,11 +86,23 @@ int64_t dagr_scan_blocks(int64_t n);
 int dagr_graph_sort(const dagr_geom_t *g, const int32_t *batch, const int32_t *pos, const float *feat,
                     int64_t N, int32_t *key, int32_t *tmp, int32_t *count, int32_t *blocksums,
                     int32_t *start, int32_t *perm, int32_t *ti, uint32_t *xyb, float *feat_s,
+                    int32_t *flags /* i32[1], zero on entry; [0]=1 if a sample is not time-sorted; may be NULL */,
                     void *stream);
 
 int dagr_graph_search(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
                       const uint32_t *xyb, int32_t *nbr, uint16_t *off, uint32_t *cellmask,
                       void *stream);
+
+/* Fused event-level build (the production path): one CTA per pool1 voxel stages the (t, arrival idx,
+ * polarity) records of the voxel's 3x3 neighbourhood in shared memory (three coalesced runs, thanks to the
+ * cell-major order), probes the spiral entirely on chip, writes the ELL adjacency + cellmask exactly like
+ * dagr_graph_search and applies conv_block1.conv_block1 (SplineConv 3->16 + BN + act, see dagr_l1_conv_a)
+ * to the neighbours as they are found -> xa f32[N,16].  cellmask needs no zeroing for this entry point. */
+struct dagr_l1a_params_s;
+int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
+                  const uint32_t *xyb, const float *feat_s, const float *tab,
+                  const struct dagr_l1a_params_s *p_host, const int32_t *flags /* from dagr_graph_sort, or NULL */,
+                  int32_t *nbr, uint16_t *off, uint32_t *cellmask, float *xa, void *stream);
 
 int dagr_graph_export(const dagr_geom_t *g, int64_t N, const int32_t *perm, const int32_t *ti,
                       const int32_t *nbr, int32_t *inv, int32_t *rowptr, int32_t *blocksums,
@@ -102,7 +116,7 @@ int dagr_graph_export(const dagr_geom_t *g, int64_t N, const int32_t *perm, cons
  * kernel slots (built from MySplineConv.init_lut's basis, spline_conv.py:27-35).
  * Weights are passed by value (constant bank): slot-major  w[u][cin][cout].
  * ------------------------------------------------------------------------------------------- */
-typedef struct {
+typedef struct dagr_l1a_params_s {
     float w[DAGR_KU][3][16];      /* weight[slot_id[u]]  (Cin = polarity, x/W, y/H)  */
     float root[3][16];            /* lin.weight^T                                    */
     float scale[16], shift[16];   /* eval BN folded: g/sqrt(v+eps), b - m*scale      */

@@ -104,6 +104,60 @@ def test_graph_hot_pixel_fifo_depth_and_small_k():
     assert int(deg.max()) == 6
 
 
+def test_dense_voxel_falls_back_to_global_probe_and_split_path_agrees():
+    """> BL_CAP staged records around one voxel exercises the global-memory fallback of the fused build
+    kernel; the v1 split kernels (graph_search + l1_conv_a) must give the same adjacency and features."""
+    from dagr_b200.data import EventBatch
+    W, H = 640, 480
+    model, args = make_model("n", H, W)
+    model.cuda()
+    g = torch.Generator().manual_seed(3)
+    n_dense, n_bg = 9000, 20000
+    x = torch.cat([torch.randint(300, 330, (n_dense,), generator=g), torch.randint(0, W, (n_bg,), generator=g)])
+    y = torch.cat([torch.randint(200, 230, (n_dense,), generator=g), torch.randint(0, H, (n_bg,), generator=g)])
+    n = n_dense + n_bg
+    t = torch.sort(torch.randint(950000, 999999, (n,), generator=g)).values
+    perm = torch.randperm(n, generator=g)
+    pos_denorm = torch.stack([x[perm], y[perm], t], 1).int()
+    p = (torch.randint(0, 2, (n,), generator=g) * 2 - 1).float().view(-1, 1)
+    data = EventBatch(x=p, pos=torch.zeros(n, 3), batch=torch.zeros(n, dtype=torch.long), width=torch.tensor([W]),
+                      height=torch.tensor([H]), time_window=torch.tensor([1000000]), pos_denorm=pos_denorm, num_graphs=1)
+    eng = model.engine
+    eng.fused_build = True
+    dec_f, batch_i, pos_i = _run_graph(model, data, 1)
+    e_f = eng.export_edges().cpu()
+    N = eng.last["N"]
+    nbr_f = eng.last["ws"]["nbr"][:16 * N].clone(); xa_f = eng.last["ws"]["xa"][:N].clone(); dec_f = dec_f.clone()
+    mask_f = eng.last["grids"][0].mask.clone()
+    eng.fused_build = False
+    dec_s, _, _ = _run_graph(model, data, 1)
+    eng.fused_build = True
+    assert torch.equal(e_f, eng.export_edges().cpu())
+    assert torch.equal(e_f, _oracle_graph(args, W, H, 1, batch_i, pos_i))
+    deg = nbr_f[15 * N:16 * N]
+    assert torch.equal(deg, eng.last["ws"]["nbr"][15 * N:16 * N])
+    assert torch.equal(mask_f, eng.last["grids"][0].mask)
+    assert_close(xa_f.cpu(), eng.last["ws"]["xa"][:N].cpu(), tol=1e-5, what="fused vs split conv_a")
+    assert_close(dec_f.cpu(), dec_s.cpu(), tol=1e-5, what="fused vs split decoded")
+
+
+def test_events_not_time_sorted_still_bit_exact():
+    """the input contract says events are time-sorted per sample; if they are not, the build kernel must
+    notice (flag from the sort) and drop its time-bucket pruning instead of returning different edges."""
+    from dagr_b200.data import EventBatch
+    W, H, n = 240, 180, 12000
+    model, args = make_model("n", H, W)
+    model.cuda()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randint(0, W, (n,), generator=g); y = torch.randint(0, H, (n,), generator=g)
+    t = torch.randint(950000, 999999, (n,), generator=g)               # NOT sorted
+    data = EventBatch(x=torch.ones(n, 1), pos=torch.zeros(n, 3), batch=torch.zeros(n, dtype=torch.long),
+                      width=torch.tensor([W]), height=torch.tensor([H]), time_window=torch.tensor([1000000]),
+                      pos_denorm=torch.stack([x, y, t], 1).int(), num_graphs=1)
+    _, batch_i, pos_i = _run_graph(model, data, 1)
+    assert torch.equal(model.engine.export_edges().cpu(), _oracle_graph(args, W, H, 1, batch_i, pos_i))
+
+
 def test_graph_empty_and_single_event():
     from dagr_b200.data import EventBatch
     W, H = 240, 180
