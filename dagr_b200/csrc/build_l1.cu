@@ -12,7 +12,7 @@
 #include "common.cuh"
 
 #define BL_THREADS 192           // >= events of a voxel at the nominal density (Poisson mean 134): one pass
-#define BL_CAP 2560              // staged neighbourhood records per CTA (uniform 300k events/sample: ~1200)
+#define BL_CAP 2048              // staged neighbourhood records per CTA (uniform 300k events/sample: ~1200)
 #define BL_NB 8                  // time buckets of width delta_t kept per tile pixel
 
 struct BLTile {
@@ -21,6 +21,14 @@ struct BLTile {
     int smin, smax;              // slice (t / delta_t) range of the voxel's own events
     int unsorted;                // some pixel's records are not time-sorted -> no time bucketing
 };
+
+__host__ __device__ __forceinline__ size_t bl_acc_offset(const dagr_geom_t &g)
+{
+    const size_t TW = g.CW + 2 * g.r, TH = g.CH + 2 * g.r, TP = TW * TH;
+    const size_t o = (size_t)BL_CAP * 12 + TP * 4 + (TW + TH) * 4 + TP * BL_NB * 2 + (size_t)g.ncell * 4 + BL_THREADS * 2 + (TW + TH);
+    return (o + 15) / 16 * 16;
+}
+static size_t bl_smem_bytes(const dagr_geom_t *g) { return bl_acc_offset(*g) + (size_t)(DAGR_ELL - 1) * BL_THREADS * 4 + 16; }
 
 #define BL_R1 96                 // spiral cells walked one-thread-per-event before unsaturated events are handed
                                  // to the warp-cooperative continuation (saturated events need ~85 cells)
@@ -34,7 +42,7 @@ struct BLTile {
 template <bool STAGED>
 __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p, bool active, const int2 me, int eb, int tidx0,
                                          int c_end, const uint32_t *s_pbin, const uint16_t *s_rng, const short *s_sp2,
-                                         const int2 *s_ti, const int2 *__restrict__ ti,
+                                         const int2 *s_ti, const int2 *__restrict__ ti, uint32_t *s_acc,
                                          int32_t *__restrict__ nbr, uint16_t *__restrict__ off, int &n_out)
 {
     const int kmax = g.K - 1;
@@ -64,8 +72,9 @@ __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p,
                     const int j = base + hi - 1 - k;
                     const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
                     if (o.y < me.y && me.x - o.x <= g.dt_us) {              // ev_graph.cu:64-69
-                        nbr[(int64_t)n * N + p] = j;                        // staged index for now; fixed up in phase B
-                        off[(int64_t)n * N + p] = (uint16_t)c;
+                        // accepted (record, cell) pairs wait in shared memory for phase B (staged mode)
+                        if (STAGED) s_acc[n * BL_THREADS + threadIdx.x] = ((uint32_t)j << 10) | (uint32_t)c;
+                        else { nbr[(int64_t)n * N + p] = j; off[(int64_t)n * N + p] = (uint16_t)c; }
                         n++;
                     }
                 }
@@ -80,7 +89,7 @@ __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p,
 template <bool STAGED>
 __device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, int p, const int2 me, int eb, int tidx0, int c_begin,
                                              int n, const uint32_t *s_pbin, const uint16_t *s_rng, const short *s_sp2,
-                                             const int2 *s_ti, const int2 *__restrict__ ti,
+                                             const int2 *s_ti, const int2 *__restrict__ ti, uint32_t *s_acc, int owner,
                                              int32_t *__restrict__ nbr, uint16_t *__restrict__ off)
 {
     const int kmax = g.K - 1;
@@ -108,8 +117,8 @@ __device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, in
                 const int j = base + hi - 1 - k;
                 const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
                 if (o.y < me.y && me.x - o.x <= g.dt_us) {
-                    nbr[(int64_t)slot * N + p] = j;
-                    off[(int64_t)slot * N + p] = (uint16_t)c;
+                    if (STAGED) s_acc[slot * BL_THREADS + owner] = ((uint32_t)j << 10) | (uint32_t)c;
+                    else { nbr[(int64_t)slot * N + p] = j; off[(int64_t)slot * N + p] = (uint16_t)c; }
                     slot++;
                 }
             }
@@ -128,10 +137,6 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BLTile T;
     __shared__ uint32_t s_mask;
-    __shared__ int s_ntodo;
-    __shared__ int4 s_ev[BL_THREADS];
-    __shared__ int s_evn[BL_THREADS];
-    __shared__ uint16_t s_todo[BL_THREADS];
     const int cell = blockIdx.x;
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
@@ -149,6 +154,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     short *s_sp = (short *)(s_rng + TPmax * BL_NB);                     // [ncell]  dx | dy << 8
     short *s_sp2 = s_sp + g.ncell;                                      // [ncell]  dy*TW + dx
     uint16_t *s_order = (uint16_t *)(s_sp2 + g.ncell);                  // [BL_THREADS]
+    uint32_t *s_acc = (uint32_t *)(smem_raw + bl_acc_offset(g));        // [K-1][BL_THREADS]  record << 10 | cell
     unsigned char *s_colv = (unsigned char *)(s_order + BL_THREADS);    // [TWmax]
     unsigned char *s_rowv = s_colv + TWmax;                             // [THmax]
 
@@ -281,8 +287,12 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
             s_order[rank] = (uint16_t)threadIdx.x;
         }
         __syncthreads();
-        const bool active = (int)threadIdx.x < chunk;
-        const int p = p0 + pb0 + (active ? (int)s_order[threadIdx.x] : 0);
+        // arrival ranks are dealt round-robin to the warps: every warp gets the same share of the old
+        // (unsaturated, slow) events of the voxel, so no warp is the straggler of the CTA
+        const int nw = blockDim.x >> 5;
+        const int rank = (int)(threadIdx.x & 31) * nw + (int)(threadIdx.x >> 5);
+        const bool active = rank < chunk;
+        const int p = p0 + pb0 + (active ? (int)s_order[rank] : 0);
         int x = 0, y = 0;
         int2 me = make_int2(0, 0);
         if (active) {
@@ -295,31 +305,24 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         if (bucketed) eb = min(max(me.x / dtw - sbase, 0), BL_NB - 1);
         int n;
         const int tidx0 = ty0 * TW + tx0;
-        if (staged) bl_probe<true>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, nbr, off, n);
-        else        bl_probe<false>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, nbr, off, n);
-        // hand events that are still unsaturated after BL_R1 cells to the warp-cooperative continuation
+        if (staged) bl_probe<true>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+        else        bl_probe<false>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+        // events still unsaturated after BL_R1 cells continue warp-cooperatively (32 cells per step), one at a time
         if (BL_R1 < g.ncell) {
-            __syncthreads();
-            if (threadIdx.x == 0) s_ntodo = 0;
-            __syncthreads();
-            s_evn[threadIdx.x] = n;
-            if (active && n < g.K - 1) {
-                s_ev[threadIdx.x] = make_int4(p, me.x, me.y, (eb << 16) | tidx0);
-                s_todo[atomicAdd(&s_ntodo, 1)] = (uint16_t)threadIdx.x;
+            unsigned todo = __ballot_sync(0xffffffffu, active && n < g.K - 1);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int ep = __shfl_sync(0xffffffffu, p, src);
+                const int2 eme = make_int2(__shfl_sync(0xffffffffu, me.x, src), __shfl_sync(0xffffffffu, me.y, src));
+                const int eeb = __shfl_sync(0xffffffffu, eb, src), etidx = __shfl_sync(0xffffffffu, tidx0, src);
+                const int en = __shfl_sync(0xffffffffu, n, src);
+                const int owner = (int)(threadIdx.x & ~31u) + src;
+                const int nn = staged ? bl_probe_coop<true>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off)
+                                      : bl_probe_coop<false>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off);
+                if ((int)(threadIdx.x & 31) == src) n = nn;
             }
-            __syncthreads();
-            const int ntodo = s_ntodo;
-            for (int i = threadIdx.x >> 5; i < ntodo; i += (blockDim.x >> 5)) {
-                const int who = s_todo[i];
-                const int4 ev = s_ev[who];
-                const int nn = staged ? bl_probe_coop<true>(g, N, ev.x, make_int2(ev.y, ev.z), ev.w >> 16, ev.w & 0xffff, BL_R1, s_evn[who],
-                                                            s_pbin, s_rng, s_sp2, s_ti, ti, nbr, off)
-                                      : bl_probe_coop<false>(g, N, ev.x, make_int2(ev.y, ev.z), ev.w >> 16, ev.w & 0xffff, BL_R1, s_evn[who],
-                                                             s_pbin, s_rng, s_sp2, s_ti, ti, nbr, off);
-                if ((threadIdx.x & 31) == 0) s_evn[who] = nn;
-            }
-            __syncthreads();
-            n = s_evn[threadIdx.x];
+            __syncwarp();
         }
         if (active) nbr[(int64_t)(DAGR_ELL - 1) * N + p] = n;
         // phase B: A_u = sum_e tab[c_e][u] * (polarity_src, x_src/W, y_src/H), converged over the ELL slots;
@@ -333,8 +336,9 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         const int nmax = __reduce_max_sync(0xffffffffu, n);
         for (int q = 0; q < nmax; q++) {
             if (q < n) {
-                const int j = nbr[(int64_t)q * N + p];
-                const int c = off[(int64_t)q * N + p];
+                int j, c;
+                if (staged) { const uint32_t a = s_acc[q * BL_THREADS + threadIdx.x]; j = (int)(a >> 10); c = (int)(a & 0x3ff); }
+                else { j = nbr[(int64_t)q * N + p]; c = off[(int64_t)q * N + p]; }
                 const int sp = s_sp[c];
                 const int tx = tx0 + (int)(signed char)(sp & 0xff), ty = ty0 + (sp >> 8);
                 const int rr = s_rowv[ty];
@@ -342,6 +346,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
                 if (staged) {
                     e0 = s_feat[j];
                     nbr[(int64_t)q * N + p] = j - T.run_off[rr] + T.run_start[rr];
+                    off[(int64_t)q * N + p] = (uint16_t)c;
                 } else e0 = __ldg(feat_s + j);
                 const int dcx = (int)s_colv[tx] - 1, dcy = rr - 1;
                 if (dcx | dcy) mloc |= 1u << ((dcy + 1) * 3 + (dcx + 1));
@@ -377,11 +382,13 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
             r = fmaf(r, P.scale[k], P.shift[k]);
             o[k] = P.relu ? fmaxf(r, 0.f) : r;
         }
-        float4 *dst = reinterpret_cast<float4 *>(xa + (int64_t)p * 16);
+        // xa is stored half-major [2][N][8] so that conv_b can stage one 32-byte channel half per pass
+        float4 *dst = reinterpret_cast<float4 *>(xa + (int64_t)p * 8);
         dst[0] = make_float4(o[0], o[1], o[2], o[3]);
         dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-        dst[2] = make_float4(o[8], o[9], o[10], o[11]);
-        dst[3] = make_float4(o[12], o[13], o[14], o[15]);
+        dst = reinterpret_cast<float4 *>(xa + (N + (int64_t)p) * 8);
+        dst[0] = make_float4(o[8], o[9], o[10], o[11]);
+        dst[1] = make_float4(o[12], o[13], o[14], o[15]);
     }
     mloc = __reduce_or_sync(0xffffffffu, mloc);
     if ((threadIdx.x & 31) == 0 && mloc) atomicOr(&s_mask, mloc);
@@ -389,11 +396,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     if (threadIdx.x == 0) cellmask[cell] = s_mask;
 }
 
-static size_t bl_smem_bytes(const dagr_geom_t *g)
-{
-    const size_t TW = g->CW + 2 * g->r, TH = g->CH + 2 * g->r, TP = TW * TH;
-    return (size_t)BL_CAP * 12 + TP * 4 + (TW + TH) * 4 + TP * BL_NB * 2 + (size_t)g->ncell * 4 + BL_THREADS * 2 + (TW + TH) + 64;
-}
+
 
 extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
                              const uint32_t *xyb, const float *feat_s, const float *tab,

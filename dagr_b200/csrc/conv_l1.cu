@@ -118,11 +118,13 @@ k_l1_conv_a(const dagr_geom_t g, int64_t N, const uint32_t *__restrict__ xyb, co
         r = fmaf(r, P.scale[k], P.shift[k]);
         o[k] = P.relu ? fmaxf(r, 0.f) : r;
     }
-    float4 *dst = reinterpret_cast<float4 *>(xa + p * 16);
+    // xa is stored half-major: [2][N][8] (channels 0-7, then 8-15), see conv_b v2
+    float4 *dst = reinterpret_cast<float4 *>(xa + p * 8);
     dst[0] = make_float4(o[0], o[1], o[2], o[3]);
     dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-    dst[2] = make_float4(o[8], o[9], o[10], o[11]);
-    dst[3] = make_float4(o[12], o[13], o[14], o[15]);
+    dst = reinterpret_cast<float4 *>(xa + (N + p) * 8);
+    dst[0] = make_float4(o[8], o[9], o[10], o[11]);
+    dst[1] = make_float4(o[12], o[13], o[14], o[15]);
 }
 
 extern "C" int dagr_l1_conv_a(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, const float *feat_s,
@@ -169,7 +171,7 @@ k_l1_conv_b(const dagr_geom_t g, int64_t N, const uint32_t *__restrict__ xyb, co
             float2 A[DAGR_KU][4];
             {
                 // self loop (spiral cell 0) and root weight: own row
-                const float4 *src = reinterpret_cast<const float4 *>(xa + p * 16 + half * 8);
+                const float4 *src = reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + p) * 8);
                 const float4 t0 = src[0], t1 = src[1];
                 const float2 v[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
                 float t[DAGR_KU];
@@ -200,7 +202,7 @@ k_l1_conv_b(const dagr_geom_t g, int64_t N, const uint32_t *__restrict__ xyb, co
             for (int q = 0; q < n; q++) {
                 const int j = nbr[(int64_t)q * N + p];
                 const int c = off[(int64_t)q * N + p];
-                const float4 *src = reinterpret_cast<const float4 *>(xa + (int64_t)j * 16 + half * 8);
+                const float4 *src = reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + j) * 8);
                 const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
                 const float2 e[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
                 float t[DAGR_KU];
@@ -290,6 +292,323 @@ extern "C" int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_l1_conv_b<<<dagr_div_up(N, L1_THREADS), L1_THREADS, smem, (cudaStream_t)stream>>>(
         *g, N, xyb, feat_s, xa, nbr, off, tab, *p_host, x1, poolmax);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// ================================================================================================
+// conv_b v2: one CTA per pool1 voxel, neighbour rows staged in shared memory by TMA bulk copies
+// ================================================================================================
+// Because nodes are stored in cell-major order, the xa rows any node of the voxel can gather are the
+// rows of its 3x3 voxel neighbourhood = THREE contiguous runs.  One elected thread issues three
+// cp.async.bulk (TMA, 1-D) copies global -> shared that complete on an mbarrier; all gathers of phase 1
+// then hit shared memory.  The per-voxel channel max, mean position and pixel rounding of pool1
+// (pooling.py:66-86) are finished in the same CTA, so neither the per-node activations nor a separate
+// finalize pass touch HBM.  Voxels whose neighbourhood exceeds the staging buffer gather from global.
+#define CB2_THREADS 160
+#define CB2_CAP 1344             // staged half-rows (32 B each) per CTA
+#define CB2_G 5                  // spline slots per pass (DAGR_KU = 3 groups of 5)
+#define CB2_NG (DAGR_KU / CB2_G)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct CB2Tile {
+    int run_start[3], run_len[3], run_off[3];
+};
+
+// One pass = one input-channel half (8 channels) x one group of 5 spline slots of one node:
+//     A_u = sum_{e in N(i) + self} tab[c_e][u] * x_e[half]      (u in the group; 5 x 8 accumulators)
+//     o  += sum_u W_u[half]^T A_u
+// `pass` is warp-uniform, so the phase-2 weights are fetched through the uniform datapath (LDCU) with a
+// run-time offset: one copy of the unrolled FFMA block serves all six passes (instruction-cache friendly),
+// and only 40 accumulators are live (no spills, higher occupancy).
+// s_ell[q][tid] = (row << 12) | spiral cell;  s_tab[g][cell][8] holds the 5 slot weights of group g.
+template <bool STAGED>
+__device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, int half, int grp, const float *__restrict__ xa, const float *s_rows,
+                                         const float *s_tab, const uint32_t *s_ell, const int32_t *__restrict__ nbr,
+                                         const uint16_t *__restrict__ off, const dagr_l1b_params_t &P, int own_row, int ncell,
+                                         float o[16])
+{
+    float2 A[CB2_G][4];
+#pragma unroll
+    for (int u = 0; u < CB2_G; u++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) A[u][k] = make_float2(0.f, 0.f);
+    const float *tabg = s_tab + (size_t)grp * ncell * 8;
+    for (int q = -1; q < n; q++) {                                       // q = -1: self loop (spiral cell 0)
+        int row, c;
+        if (q < 0) { row = STAGED ? own_row : p; c = 0; }
+        else if (STAGED) {
+            const uint32_t ell = s_ell[q * CB2_THREADS + threadIdx.x];
+            row = (int)(ell >> 12); c = (int)(ell & 0xfff);
+        } else {
+            row = nbr[(int64_t)q * N + p]; c = off[(int64_t)q * N + p];
+        }
+        const float4 *src = STAGED ? reinterpret_cast<const float4 *>(s_rows + (int64_t)row * 8)
+                                   : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + row) * 8);
+        const float4 t0 = src[0], t1 = src[1];
+        const float2 e[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
+        const float4 w0 = *reinterpret_cast<const float4 *>(tabg + c * 8);
+        const float w4 = tabg[c * 8 + 4];
+        const float t[CB2_G] = {w0.x, w0.y, w0.z, w0.w, w4};
+#pragma unroll
+        for (int u = 0; u < CB2_G; u++) {
+            const float2 tt = make_float2(t[u], t[u]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) A[u][k] = ffma2(tt, e[k], A[u][k]);
+        }
+    }
+    const float (*W)[16][16] = &P.w[grp * CB2_G];
+#pragma unroll
+    for (int u = 0; u < CB2_G; u++)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                o[c] = fmaf(A[u][k].x, W[u][8 * half + 2 * k][c], o[c]);
+                o[c] = fmaf(A[u][k].y, W[u][8 * half + 2 * k + 1][c], o[c]);
+            }
+}
+
+__device__ __forceinline__ float cb2_div_floor(float a, float b)
+{
+    const float mod = fmodf(a, b);
+    float div = __fdiv_rn(__fsub_rn(a, mod), b);
+    if ((mod != 0.f) && ((b < 0.f) != (mod < 0.f))) div -= 1.f;
+    float fl;
+    if (div != 0.f) { fl = floorf(div); if (div - fl > 0.5f) fl += 1.f; }
+    else fl = copysignf(0.f, __fdiv_rn(a, b));
+    return fl;
+}
+__device__ __forceinline__ int cb2_round_to_pixel(float mean, int size)
+{
+    const float inv = __frcp_rn((float)size);
+    const int k = (int)cb2_div_floor(__fadd_rn(mean, 1e-5f), inv);
+    return min(max(k, 0), size - 1);
+}
+
+__global__ void __launch_bounds__(CB2_THREADS, 3)
+k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
+             const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
+             const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off, const float *__restrict__ tab,
+             const __grid_constant__ dagr_l1b_params_t P, float *__restrict__ x1, int32_t *__restrict__ cnt,
+             int32_t *__restrict__ pxy, float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ CB2Tile T;
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ float s_red[CB2_THREADS / 32][16];
+    __shared__ long long s_sum[CB2_THREADS / 32][3];
+    __shared__ int s_tm[CB2_THREADS / 32];
+    float *s_rows = (float *)smem_raw;                                   // [CB2_CAP][8]   one channel half of the 3 runs
+    float *s_tab = s_rows + (size_t)CB2_CAP * 8;                         // [CB2_NG][ncell][8]
+    uint32_t *s_ell = (uint32_t *)(s_tab + (size_t)CB2_NG * g.ncell * 8);// [15][CB2_THREADS]
+    const int cell = blockIdx.x;
+    const int per = g.ny1 * g.nx1;
+    const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
+    const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
+    const int nown = p1 - p0;
+    if (nown == 0) {                                                     // block-uniform
+        if (threadIdx.x == 0) { cnt[cell] = 0; pxy[2 * cell] = 0; pxy[2 * cell + 1] = 0; tmean[cell] = 0.f; tmax[cell] = 0.f; }
+        if (threadIdx.x < 16) xg[(int64_t)cell * 16 + threadIdx.x] = 0.f;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const int clo = max(cx - 1, 0), chi = min(cx + 1, g.nx1 - 1);
+        int o = 0;
+        for (int rr = 0; rr < 3; rr++) {
+            const int ry = cy - 1 + rr;
+            if (ry < 0 || ry >= g.ny1) { T.run_start[rr] = 0; T.run_len[rr] = 0; T.run_off[rr] = o; continue; }
+            const int64_t c0 = (int64_t)b * per + ry * g.nx1 + clo, c1 = (int64_t)b * per + ry * g.nx1 + chi + 1;
+            const int s = start[c0 * g.CP], e = start[c1 * g.CP];
+            T.run_start[rr] = s; T.run_len[rr] = e - s; T.run_off[rr] = o;
+            o += e - s;
+        }
+        mbar_init(&s_bar, 1);
+    }
+    // slot-weight table regrouped as [group][cell][8] (5 used) so one pass reads two aligned vectors per edge
+    for (int i = threadIdx.x; i < g.ncell * 4; i += blockDim.x) {
+        const int c = i >> 2, v = i & 3;
+        const float4 t4 = __ldg(reinterpret_cast<const float4 *>(tab + c * DAGR_TABW) + v);
+        const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int u = v * 4 + k;
+            if (u < DAGR_KU) s_tab[((size_t)(u / CB2_G) * g.ncell + c) * 8 + (u % CB2_G)] = tv[k];
+        }
+    }
+    __syncthreads();
+    const int total = T.run_off[2] + T.run_len[2];
+    const bool staged = total <= CB2_CAP;                                // block-uniform
+    const int s1 = T.run_start[1];
+    const int s2 = T.run_len[2] > 0 ? T.run_start[2] : 0x7fffffff;
+    const int d0 = T.run_off[0] - T.run_start[0], d1 = T.run_off[1] - T.run_start[1], d2 = T.run_off[2] - T.run_start[2];
+
+    float m[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) m[c] = -INFINITY;
+    long long sx = 0, sy = 0, st = 0;
+    int tm = -2147483647;
+    uint32_t parity = 0;
+    for (int pb0 = p0; pb0 < p1; pb0 += blockDim.x) {
+        const int p = pb0 + threadIdx.x;
+        const bool active = p < p1;
+        const int n = active ? nbr[(int64_t)(DAGR_ELL - 1) * N + p] : 0;
+        // stage this node's ELL row (independent loads -> one global latency); neighbour positions become staged rows
+        if (staged && active) {
+            int jj[DAGR_ELL - 1]; int cc[DAGR_ELL - 1];
+#pragma unroll
+            for (int q = 0; q < DAGR_ELL - 1; q++) {
+                jj[q] = (q < n) ? nbr[(int64_t)q * N + p] : 0;
+                cc[q] = (q < n) ? (int)off[(int64_t)q * N + p] : 0;
+            }
+#pragma unroll
+            for (int q = 0; q < DAGR_ELL - 1; q++) {
+                const int j = jj[q];
+                const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
+                s_ell[q * CB2_THREADS + threadIdx.x] = ((uint32_t)row << 12) | (uint32_t)cc[q];
+            }
+        }
+        float o[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) o[k] = 0.f;
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            if (staged) {
+                __syncthreads();                                        // everyone is done with the previous half's rows
+                if (threadIdx.x == 0) {
+                    // TMA: three contiguous runs of 32-byte half-rows, global -> shared, completion on the mbarrier
+                    mbar_expect_tx(&s_bar, (uint32_t)total * 32u);
+                    for (int rr = 0; rr < 3; rr++)
+                        if (T.run_len[rr] > 0)
+                            tma_bulk_g2s(s_rows + (size_t)T.run_off[rr] * 8, xa + ((size_t)half * N + T.run_start[rr]) * 8,
+                                         (uint32_t)T.run_len[rr] * 32u, &s_bar);
+                }
+                mbar_wait(&s_bar, parity);
+                parity ^= 1;
+            }
+            if (active) {
+                // root weight on this half of x_i
+                {
+                    const float4 *src = staged ? reinterpret_cast<const float4 *>(s_rows + (int64_t)(p + d1) * 8)
+                                               : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + p) * 8);
+                    const float4 t0 = src[0], t1 = src[1];
+                    const float v[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+#pragma unroll
+                        for (int c = 0; c < 16; c++) o[c] = fmaf(v[k], P.root[8 * half + k][c], o[c]);
+                }
+#pragma unroll 1
+                for (int grp = 0; grp < CB2_NG; grp++) {
+                    if (staged) cb2_pass<true>(N, p, n, half, grp, xa, s_rows, s_tab, s_ell, nbr, off, P, p + d1, g.ncell, o);
+                    else        cb2_pass<false>(N, p, n, half, grp, xa, s_rows, s_tab, s_ell, nbr, off, P, 0, g.ncell, o);
+                }
+            }
+        }
+        if (!active) continue;
+        const uint32_t w = xyb[p];
+        const int x = w & 0xfff, y = (w >> 12) & 0xfff;
+        const float f0 = feat_s[p], f1 = __ldg(g.posx0 + x), f2 = __ldg(g.posy0 + y);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            float sk = f0 * P.skip[0][c];
+            sk = fmaf(f1, P.skip[1][c], sk);
+            sk = fmaf(f2, P.skip[2][c], sk);
+            sk = fmaf(sk, P.sscale[c], P.sshift[c]);
+            float r = fmaf(o[c], P.scale[c], P.shift[c]) + sk;
+            r = P.relu ? fmaxf(r, 0.f) : r;
+            o[c] = r;
+            m[c] = fmaxf(m[c], r);
+        }
+        if (x1 != nullptr) {
+            float4 *dst = reinterpret_cast<float4 *>(x1 + (int64_t)p * 16);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+            dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+            dst[3] = make_float4(o[12], o[13], o[14], o[15]);
+        }
+        const int t = ti[p].x;
+        sx += x; sy += y; st += t; tm = max(tm, t);
+    }
+    // ---- pool1: per-voxel max / mean position (pooling.py:66-86) -------------------------------------
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) m[c] = fmaxf(m[c], __shfl_xor_sync(0xffffffffu, m[c], d));
+        sx += __shfl_xor_sync(0xffffffffu, sx, d);
+        sy += __shfl_xor_sync(0xffffffffu, sy, d);
+        st += __shfl_xor_sync(0xffffffffu, st, d);
+        tm = max(tm, __shfl_xor_sync(0xffffffffu, tm, d));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) s_red[wid][c] = m[c];
+        s_sum[wid][0] = sx; s_sum[wid][1] = sy; s_sum[wid][2] = st; s_tm[wid] = tm;
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    if (threadIdx.x < 16) {
+        float v = s_red[0][threadIdx.x];
+        for (int w2 = 1; w2 < nw; w2++) v = fmaxf(v, s_red[w2][threadIdx.x]);
+        xg[(int64_t)cell * 16 + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 32) {
+        long long ax = 0, ay = 0, at = 0; int tmx = -2147483647;
+        for (int w2 = 0; w2 < nw; w2++) { ax += s_sum[w2][0]; ay += s_sum[w2][1]; at += s_sum[w2][2]; tmx = max(tmx, s_tm[w2]); }
+        const float mx = (float)((double)ax / ((double)nown * (double)g.W));
+        const float my = (float)((double)ay / ((double)nown * (double)g.H));
+        cnt[cell] = nown;
+        pxy[2 * cell] = cb2_round_to_pixel(mx, g.W);
+        pxy[2 * cell + 1] = cb2_round_to_pixel(my, g.H);
+        tmean[cell] = (float)((double)at / ((double)nown * (double)g.T));
+        tmax[cell] = __fdiv_rn((float)tmx, (float)g.T);
+    }
+}
+
+extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
+                                         const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
+                                         const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
+                                         float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg,
+                                         void *stream)
+{
+    DAGR_CHECK_ARG(g && p_host, "null argument");
+    const int cells = g->B * g->ny1 * g->nx1;
+    DAGR_CHECK_ARG(g->ncell <= 4096, "spiral cell index must fit 12 bits");
+    const size_t smem = (size_t)CB2_CAP * 32 + (size_t)CB2_NG * g->ncell * 8 * 4 + (size_t)(DAGR_ELL - 1) * CB2_THREADS * 4;
+    DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    k_l1_conv_b2<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, tab,
+                                                                     *p_host, x1, cnt, pxy, tmean, tmax, xg);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

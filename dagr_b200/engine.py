@@ -76,13 +76,14 @@ class Engine:
         self._pack_key = None
         self._ws: Dict[tuple, dict] = {}
         self.keep_node_features = False      # debug / parity: materialise per-event activations
+        self.voxel_conv_b = True             # conv_b + pool1 as one CTA per voxel with TMA-staged rows (False: v1)
         self.fused_build = True              # probe + conv_a in one shared-memory-tiled kernel (False: v1 split kernels)
         self.last = {}
         self.launches = 0                    # kernels of libdagr_b200.so enqueued so far
         self.prof = None                     # dict name -> [(start_evt, end_evt)] when per-op timing is on
 
     # kernels enqueued by each C-ABI call (see csrc/*.cu)
-    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1,
+    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=1,
                      dagr_pool1_finalize=1, dagr_grid_cat_pos=1, dagr_grid_conv=1, dagr_grid_linear_bn=1, dagr_grid_pool=1,
                      dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1,
                      dagr_postprocess_nms=1, dagr_sample_features=1, dagr_denormalize_pos=1)
@@ -186,7 +187,7 @@ class Engine:
             ws["feat_s"] = torch.empty(cap, dtype=torch.float32, device=dev)
             ws["nbr"] = torch.empty(_lib.ELL * cap, dtype=torch.int32, device=dev)
             ws["off"] = torch.empty(_lib.ELL * cap, dtype=torch.int16, device=dev)
-            ws["xa"] = torch.empty((cap, 16), dtype=torch.float32, device=dev)
+            ws["xa"] = torch.empty(cap * 16, dtype=torch.float32, device=dev)      # half-major [2][N][8]
             ws["x1"] = None
             # zero-on-entry accumulators of all levels in ONE buffer (single memset per forward)
             C_lv = self.model.backbone.output_channels          # [16, 64, C, C, C]
@@ -333,14 +334,19 @@ class Engine:
             if ws["x1"] is None or ws["x1"].shape[0] < ws["cap"]:
                 ws["x1"] = torch.empty((ws["cap"], 16), dtype=torch.float32, device=dev)
             x1 = ws["x1"]
-        self._run("l1_conv_b_pool", lib.dagr_l1_conv_b_pool, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]),
-                                           _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]),
-                                           _lib.ptr(x1), _lib.ptr(poolmax), st)
         g1: GridState = ws["grids"][0]
         g1.x = self._buf(ws, "gx0", (g1.cells, 16), torch.float32, dev)
-        self._run("pool1_finalize", lib.dagr_pool1_finalize, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(ws["ti"]),
-                                           _lib.ptr(poolmax), 16, _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean),
-                                           _lib.ptr(g1.tmax), _lib.ptr(g1.x), st)
+        if self.voxel_conv_b:
+            self._run("l1_conv_b_pool_voxel", lib.dagr_l1_conv_b_pool_voxel, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]),
+                      _lib.ptr(ws["ti"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]), _lib.ptr(nbr), _lib.ptr(off),
+                      _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(x1), _lib.ptr(g1.cnt), _lib.ptr(g1.pxy),
+                      _lib.ptr(g1.tmean), _lib.ptr(g1.tmax), _lib.ptr(g1.x), st)
+        else:
+            self._run("l1_conv_b_pool", lib.dagr_l1_conv_b_pool, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]),
+                      _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(x1), _lib.ptr(poolmax), st)
+            self._run("pool1_finalize", lib.dagr_pool1_finalize, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(ws["ti"]),
+                      _lib.ptr(poolmax), 16, _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean), _lib.ptr(g1.tmax),
+                      _lib.ptr(g1.x), st)
         g1.mask = cellmask[:g1.cells]
         if kto:
             self._run("temporal_filter", lib.dagr_grid_temporal_filter, C.byref(geom.levels[0].grid), _lib.ptr(g1.cnt), _lib.ptr(g1.tmax),
@@ -393,6 +399,13 @@ class Engine:
             dense_all.append(dense)
         self.last = dict(geom=geom, ws=ws, N=N, grids=[g1, g2, g3, g4], inter=inter, dense=dense_all, x1=x1)
         return out
+
+    def xa_rows(self):
+        """conv_block1.conv_block1 activations of the last forward as [N,16] rows in sorted order
+        (the kernels keep them half-major, [2][N][8])."""
+        L = self.last
+        N, xa = L["N"], L["ws"]["xa"]
+        return torch.cat([xa[:N * 8].view(N, 8), xa[N * 8:2 * N * 8].view(N, 8)], dim=1)
 
     @torch.no_grad()
     def postprocess(self, decoded: torch.Tensor, conf_thre, nms_thre, width, height, filtering=True):

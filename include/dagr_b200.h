@@ -143,6 +143,16 @@ int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, co
                         const float *xa, const int32_t *nbr, const uint16_t *off, const float *tab,
                         const dagr_l1b_params_t *p_host, float *x1, uint32_t *poolmax, void *stream);
 
+/* Production form of conv_b: one CTA per pool1 voxel; the xa rows of the voxel's 3x3 neighbourhood (three
+ * contiguous runs in cell-major order) are staged in shared memory with TMA bulk copies (cp.async.bulk
+ * + mbarrier) and pool1 is finished in the same CTA (replaces dagr_l1_conv_b_pool + dagr_pool1_finalize):
+ * -> cnt i32[cells], pxy i32[cells,2], tmean/tmax f32[cells], xg f32[cells,16]; x1 optional as above. */
+int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
+                              const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
+                              const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
+                              float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg,
+                              void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Coarse levels live on dense voxel grids [B, ny, nx]: per cell  valid, pixel position, features,
  * and an 8-neighbour in-edge mask (bit (dcy+1)*3+(dcx+1), src cell = dst cell + (dcx,dcy)).

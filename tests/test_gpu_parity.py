@@ -127,7 +127,7 @@ def test_dense_voxel_falls_back_to_global_probe_and_split_path_agrees():
     dec_f, batch_i, pos_i = _run_graph(model, data, 1)
     e_f = eng.export_edges().cpu()
     N = eng.last["N"]
-    nbr_f = eng.last["ws"]["nbr"][:16 * N].clone(); xa_f = eng.last["ws"]["xa"][:N].clone(); dec_f = dec_f.clone()
+    nbr_f = eng.last["ws"]["nbr"][:16 * N].clone(); xa_f = eng.xa_rows().clone(); dec_f = dec_f.clone()
     mask_f = eng.last["grids"][0].mask.clone()
     eng.fused_build = False
     dec_s, _, _ = _run_graph(model, data, 1)
@@ -137,7 +137,7 @@ def test_dense_voxel_falls_back_to_global_probe_and_split_path_agrees():
     deg = nbr_f[15 * N:16 * N]
     assert torch.equal(deg, eng.last["ws"]["nbr"][15 * N:16 * N])
     assert torch.equal(mask_f, eng.last["grids"][0].mask)
-    assert_close(xa_f.cpu(), eng.last["ws"]["xa"][:N].cpu(), tol=1e-5, what="fused vs split conv_a")
+    assert_close(xa_f.cpu(), eng.xa_rows().cpu(), tol=1e-5, what="fused vs split conv_a")
     assert_close(dec_f.cpu(), dec_s.cpu(), tol=1e-5, what="fused vs split decoded")
 
 
@@ -229,7 +229,7 @@ def test_forward_parity_vs_oracle(W, H, B, n, kind, size, dataset):
     # event level: edges bit-exact, features within tolerance (arrival order)
     assert torch.equal(eng.export_edges().cpu(), o["edge_index"])
     perm = L["ws"]["perm"]
-    xa = export.unsort_rows(L["ws"]["xa"], perm, N).cpu()
+    xa = export.unsort_rows(eng.xa_rows(), perm, N).cpu()
     x1 = export.unsort_rows(L["x1"], perm, N).cpu()
     assert_close(xa, o["x1a"], what="conv_block1.conv_block1 output")
     assert_close(x1, o["x1"], what="conv_block1 output")
