@@ -196,6 +196,185 @@ k_grid_conv(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2: split-K SplineConv on a voxel grid.  One CTA handles CPB consecutive voxels with 8 warps:
+//   phase 1  A[k][c][j] = sum_{in-edges e of voxel j} b_k(e) * x[src_e][c]   (k < 25), A[25] = x[j] (root)
+//            built once in shared memory (each thread owns (voxel, channel) pairs: no races);
+//   phase 2  warp w accumulates the slots k = w, w+8, ... : lanes run over output channels (coalesced
+//            weight rows from L2), every weight is reused for all CPB voxels (A read as float4 broadcasts);
+//   phase 3  the 8 partial sums meet in shared memory; bias, folded BN, residual and relu in the epilogue.
+// The serial depth per lane drops from 25*Cin to ~3.3*Cin and each weight is fetched once per CPB voxels.
+// ------------------------------------------------------------------------------------------------
+#define SK_WARPS 8
+#define SK_SLOTS 26
+
+template <int CPB>
+__global__ void __launch_bounds__(SK_WARPS * 32)
+k_grid_conv_sk(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t *__restrict__ pxy,
+               const uint32_t *__restrict__ mask, const float *__restrict__ xin, int Cin, int Cout,
+               const float *__restrict__ weight, const float *__restrict__ rootT, const float *__restrict__ bias,
+               const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ skip,
+               int relu, float den_x, float den_y, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float smem_f[];
+    float *A = smem_f;                                         // [26][Cin][CPB]
+    // [SK_WARPS][CPB][Cout]; aliases A when there is a single 64-wide output tile (A is dead after phase 2)
+    float *part = (Cout <= 64) ? A : A + (size_t)SK_SLOTS * Cin * CPB;
+    __shared__ int s_src[CPB][8];
+    __shared__ float s_w[CPB][8][4];
+    __shared__ unsigned char s_slot[CPB][8][4];
+    __shared__ int s_ne[CPB];
+    __shared__ unsigned int s_used;
+    const int cells = gr.B * gr.ny * gr.nx;
+    const int cell0 = blockIdx.x * CPB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = gr.ny * gr.nx;
+
+    if (tid == 0) s_used = 0;
+    for (int i = tid; i < SK_SLOTS * Cin * CPB; i += blockDim.x) A[i] = 0.f;
+    __syncthreads();
+    // ---- edge tables: one thread per (voxel, neighbour bit) ---------------------------------------------
+    if (tid < CPB * 9) {
+        const int j = tid / 9, bit = tid % 9;
+        const int cell = cell0 + j;
+        if (bit == 4) {
+            // slot bookkeeping done by the other lanes; this lane counts the edges afterwards
+        } else if (cell < cells && cnt[cell] > 0 && ((mask[cell] >> bit) & 1u)) {
+            const int b = cell / per, rem = cell % per, cy = rem / gr.nx, cx = rem % gr.nx;
+            const int sx = cx + bit % 3 - 1, sy = cy + bit / 3 - 1;
+            if (sx >= 0 && sy >= 0 && sx < gr.nx && sy < gr.ny) {
+                const int src = b * per + sy * gr.nx + sx;
+                if (cnt[src] > 0) {
+                    const int dx = pxy[2 * src] - pxy[2 * cell], dy = pxy[2 * src + 1] - pxy[2 * cell + 1];
+                    const float ax = __fadd_rn(__fdiv_rn((float)dx, den_x), 0.5f);
+                    const float ay = __fadd_rn(__fdiv_rn((float)dy, den_y), 0.5f);
+                    float w[4]; int slot[4];
+                    spline_basis2(ax, ay, 5, w, slot);
+                    const int e = bit < 4 ? bit : bit - 1;              // dense edge index 0..7
+                    s_src[j][e] = src;
+                    unsigned int used = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { s_w[j][e][q] = w[q]; s_slot[j][e][q] = (unsigned char)slot[q]; if (w[q] != 0.f) used |= 1u << slot[q]; }
+                    atomicOr(&s_used, used);
+                    goto table_done;
+                }
+            }
+            { const int e = bit < 4 ? bit : bit - 1; s_src[j][e] = -1; }
+        } else {
+            const int e = bit < 4 ? bit : bit - 1;
+            if (bit != 4) s_src[j][e] = -1;
+        }
+    }
+table_done:
+    __syncthreads();
+    // ---- phase 1: A[k][c][j] --------------------------------------------------------------------------------
+    for (int i = tid; i < CPB * Cin; i += blockDim.x) {
+        const int j = i / Cin, c = i % Cin;
+        const int cell = cell0 + j;
+        if (cell >= cells || cnt[cell] <= 0) continue;
+        A[((size_t)25 * Cin + c) * CPB + j] = xin[(int64_t)cell * Cin + c];          // root "slot"
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int src = s_src[j][e];
+            if (src < 0) continue;
+            const float v = xin[(int64_t)src * Cin + c];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float *a = A + ((size_t)s_slot[j][e][q] * Cin + c) * CPB + j;
+                *a = fmaf(s_w[j][e][q], v, *a);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: split-K over slots ---------------------------------------------------------------------------
+    const unsigned int used = s_used | (1u << 25);
+    for (int o0 = 0; o0 < Cout; o0 += 64) {
+        float acc[2][CPB];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int j = 0; j < CPB; j++) acc[h][j] = 0.f;
+        const int oa = o0 + lane, ob = o0 + 32 + lane;
+        for (int k = warp; k < SK_SLOTS; k += SK_WARPS) {
+            if (!((used >> k) & 1u)) continue;
+            const float *wk = (k < 25) ? weight + (int64_t)k * Cin * Cout : rootT;
+            const float *ak = A + (size_t)k * Cin * CPB;
+            // weights are fetched in batches of 8 rows (16 independent loads in flight) before the FMAs: the
+            // loop is otherwise one exposed L2 round trip per row
+            for (int c0 = 0; c0 < Cin; c0 += 8) {
+                float wa[8], wb[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int c = c0 + u;
+                    wa[u] = (c < Cin && oa < Cout) ? __ldg(wk + (int64_t)c * Cout + oa) : 0.f;
+                    wb[u] = (c < Cin && ob < Cout) ? __ldg(wk + (int64_t)c * Cout + ob) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int c = min(c0 + u, Cin - 1);                  // clamped rows carry zero weights
+                    if (CPB % 4 == 0) {
+#pragma unroll
+                        for (int j4 = 0; j4 < CPB / 4; j4++) {
+                            const float4 a4 = *reinterpret_cast<const float4 *>(ak + (size_t)c * CPB + 4 * j4);
+                            acc[0][4 * j4 + 0] = fmaf(a4.x, wa[u], acc[0][4 * j4 + 0]); acc[1][4 * j4 + 0] = fmaf(a4.x, wb[u], acc[1][4 * j4 + 0]);
+                            acc[0][4 * j4 + 1] = fmaf(a4.y, wa[u], acc[0][4 * j4 + 1]); acc[1][4 * j4 + 1] = fmaf(a4.y, wb[u], acc[1][4 * j4 + 1]);
+                            acc[0][4 * j4 + 2] = fmaf(a4.z, wa[u], acc[0][4 * j4 + 2]); acc[1][4 * j4 + 2] = fmaf(a4.z, wb[u], acc[1][4 * j4 + 2]);
+                            acc[0][4 * j4 + 3] = fmaf(a4.w, wa[u], acc[0][4 * j4 + 3]); acc[1][4 * j4 + 3] = fmaf(a4.w, wb[u], acc[1][4 * j4 + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CPB; j++) {
+                            const float a = ak[(size_t)c * CPB + j];
+                            acc[0][j] = fmaf(a, wa[u], acc[0][j]); acc[1][j] = fmaf(a, wb[u], acc[1][j]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- phase 3: reduce the 8 partial sums, epilogue ---------------------------------------------------------
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < CPB; j++) {
+            if (oa < Cout) part[((size_t)warp * CPB + j) * Cout + oa] = acc[0][j];
+            if (ob < Cout) part[((size_t)warp * CPB + j) * Cout + ob] = acc[1][j];
+        }
+        __syncthreads();
+        const int ow = min(64, Cout - o0);
+        for (int i = tid; i < CPB * ow; i += blockDim.x) {
+            const int j = i / ow, o = o0 + i % ow;
+            const int cell = cell0 + j;
+            if (cell >= cells) continue;
+            float v = 0.f;
+            if (cnt[cell] > 0) {
+#pragma unroll
+                for (int w2 = 0; w2 < SK_WARPS; w2++) v += part[((size_t)w2 * CPB + j) * Cout + o];
+                if (bias) v += bias[o];
+                if (scale) v = fmaf(v, scale[o], shift[o]);
+                if (skip) v += skip[(int64_t)cell * Cout + o];
+                if (relu) v = fmaxf(v, 0.f);
+            }
+            out[(int64_t)cell * Cout + o] = v;
+        }
+    }
+}
+
+template <int CPB>
+static int launch_grid_conv_sk(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const uint32_t *mask,
+                               const float *xin, int Cin, int Cout, const float *weight, const float *rootT, const float *bias,
+                               const float *scale, const float *shift, const float *skip, int relu, float den_x, float den_y,
+                               float *out, cudaStream_t st)
+{
+    const int cells = gr->B * gr->ny * gr->nx;
+    const size_t a_bytes = (size_t)SK_SLOTS * Cin * CPB * sizeof(float), p_bytes = (size_t)SK_WARPS * CPB * Cout * sizeof(float);
+    const size_t smem = (Cout <= 64) ? (a_bytes > p_bytes ? a_bytes : p_bytes) : a_bytes + p_bytes;
+    if (smem > 200 * 1024) return -1;
+    cudaError_t e = cudaFuncSetAttribute(k_grid_conv_sk<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -2;
+    k_grid_conv_sk<CPB><<<dagr_div_up(cells, CPB), SK_WARPS * 32, smem, st>>>(*gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias,
+                                                                            scale, shift, skip, relu, den_x, den_y, out);
+    return 0;
+}
+
 extern "C" int dagr_grid_conv(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const uint32_t *mask,
                               const float *xin, int Cin, int Cout, const float *weight, const float *rootT,
                               const float *bias, const float *scale, const float *shift, const float *skip, int relu,
@@ -203,11 +382,24 @@ extern "C" int dagr_grid_conv(const dagr_grid_t *gr, const int32_t *cnt, const i
 {
     DAGR_CHECK_ARG(gr && Cin > 0 && Cout > 0, "bad channels");
     const int cells = gr->B * gr->ny * gr->nx;
-    const size_t smem = (size_t)GC_WARPS * GC_SLOTS * Cin * sizeof(float);
-    DAGR_CHECK_ARG(smem <= 200 * 1024, "Cin too large for the grid conv kernel");
-    DAGR_CUDA(cudaFuncSetAttribute(k_grid_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_grid_conv<<<dagr_div_up(cells, GC_WARPS), GC_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        *gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out);
+    cudaStream_t st = (cudaStream_t)stream;
+    // voxels per CTA: enough CTAs to fill 148 SMs, as much weight reuse as shared memory allows
+    int rc = -1;
+    const size_t per_cell = ((size_t)SK_SLOTS * Cin + (Cout <= 64 ? 0 : (size_t)SK_WARPS * Cout)) * sizeof(float);
+    if (cells >= 148 * 16 * 2 && per_cell * 16 <= 110 * 1024)
+        rc = launch_grid_conv_sk<16>(gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
+    if (rc != 0 && cells >= 148 * 4 && per_cell * 4 <= 160 * 1024)
+        rc = launch_grid_conv_sk<4>(gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
+    if (rc != 0)
+        rc = launch_grid_conv_sk<1>(gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
+    if (rc != 0) {
+        // very wide layers: v1 kernel (one warp per voxel)
+        const size_t smem = (size_t)GC_WARPS * GC_SLOTS * Cin * sizeof(float);
+        DAGR_CHECK_ARG(smem <= 200 * 1024, "Cin too large for the grid conv kernels");
+        DAGR_CUDA(cudaFuncSetAttribute(k_grid_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_grid_conv<<<dagr_div_up(cells, GC_WARPS), GC_WARPS * 32, smem, st>>>(
+            *gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out);
+    }
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }
@@ -431,7 +623,7 @@ extern "C" int dagr_head_decode(const float *reg, const float *obj, const float 
     return DAGR_OK;
 }
 
-#define NMS_MAX 1024
+#define NMS_MAX 256
 __global__ void __launch_bounds__(256)
 k_postprocess_nms(const float *__restrict__ pred, int A, int nc, float conf_thre, float nms_thre, float max_dim1,
                   int filtering, float *__restrict__ det, int32_t *__restrict__ ndet)
@@ -476,25 +668,39 @@ k_postprocess_nms(const float *__restrict__ pred, int A, int nc, float conf_thre
     }
     __syncthreads();
     const int n = ncand;
-    // greedy suppression in score order (torchvision.ops.nms semantics)
-    for (int i = 0; i < n; i++) {
+    // greedy suppression in score order (torchvision.ops.nms semantics): every candidate first computes, in
+    // parallel, the bitmask of lower-ranked candidates it would suppress; one thread then walks the ranking.
+    __shared__ uint32_t supp[NMS_MAX][NMS_MAX / 32];
+    const int nwords = (n + 31) / 32;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int ai = order[i];
-        if (alive[ai]) {                                    // uniform across the block (shared)
-            const float ax1 = bx[ai][0], ay1 = bx[ai][1], ax2 = bx[ai][2], ay2 = bx[ai][3];
-            const float sa = (ax2 - ax1) * (ay2 - ay1);
-            for (int k = i + 1 + threadIdx.x; k < n; k += blockDim.x) {
+        const float ax1 = bx[ai][0], ay1 = bx[ai][1], ax2 = bx[ai][2], ay2 = bx[ai][3];
+        const float sa = (ax2 - ax1) * (ay2 - ay1);
+        for (int wd = 0; wd < nwords; wd++) {
+            uint32_t bits = 0;
+            for (int k = wd * 32; k < min(n, wd * 32 + 32); k++) {
+                if (k <= i) continue;
                 const int aj = order[k];
-                if (!alive[aj]) continue;
                 const float l = fmaxf(ax1, bx[aj][0]), t = fmaxf(ay1, bx[aj][1]);
                 const float r = fminf(ax2, bx[aj][2]), bt = fminf(ay2, bx[aj][3]);
                 const float iw = fmaxf(r - l, 0.f), ih = fmaxf(bt - t, 0.f);
                 const float inter = iw * ih;
                 const float sb = (bx[aj][2] - bx[aj][0]) * (bx[aj][3] - bx[aj][1]);
-                if (inter / (sa + sb - inter) > nms_thre) alive[aj] = 0;
+                if (inter / (sa + sb - inter) > nms_thre) bits |= 1u << (k & 31);
             }
+            supp[i][wd] = bits;
         }
-        __syncthreads();
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t dead[NMS_MAX / 32];
+        for (int wd = 0; wd < nwords; wd++) dead[wd] = 0;
+        for (int i = 0; i < n; i++) {
+            if ((dead[i >> 5] >> (i & 31)) & 1u) { alive[order[i]] = 0; continue; }
+            for (int wd = i >> 5; wd < nwords; wd++) dead[wd] |= supp[i][wd];
+        }
+    }
+    __syncthreads();
     // compact survivors in score order; stage through shared (reuse bx rows as 6-float records is too small) ->
     // serial compaction by one warp keeps it simple (A <= 1024)
     __shared__ float stage[NMS_MAX][6];
@@ -515,7 +721,7 @@ k_postprocess_nms(const float *__restrict__ pred, int A, int nc, float conf_thre
 extern "C" int dagr_postprocess_nms(const float *pred, int B, int A, int nc, float conf_thre, float nms_thre, int width,
                                     int height, int filtering, float *det, int32_t *ndet, void *stream)
 {
-    DAGR_CHECK_ARG(A > 0 && A <= NMS_MAX, "A must be in [1,1024]");
+    DAGR_CHECK_ARG(A > 0 && A <= NMS_MAX, "A must be in [1,256] (two-scale DAGR heads have 175 anchors)");
     const float max_dim1 = (float)((width > height ? width : height) + 1);
     k_postprocess_nms<<<B, 256, 0, (cudaStream_t)stream>>>(pred, A, nc, conf_thre, nms_thre, max_dim1, filtering, det, ndet);
     DAGR_CHECK_LAUNCH();

@@ -355,7 +355,7 @@ template <bool STAGED>
 __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, int half, int grp, const float *__restrict__ xa, const float *s_rows,
                                          const float *s_tab, const uint32_t *s_ell, const int32_t *__restrict__ nbr,
                                          const uint16_t *__restrict__ off, const dagr_l1b_params_t &P, int own_row, int ncell,
-                                         float o[16])
+                                         float2 o2[8])
 {
     float2 A[CB2_G][4];
 #pragma unroll
@@ -392,9 +392,10 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, int half, int 
 #pragma unroll
         for (int k = 0; k < 4; k++)
 #pragma unroll
-            for (int c = 0; c < 16; c++) {
-                o[c] = fmaf(A[u][k].x, W[u][8 * half + 2 * k][c], o[c]);
-                o[c] = fmaf(A[u][k].y, W[u][8 * half + 2 * k + 1][c], o[c]);
+            for (int c = 0; c < 8; c++) {
+                // packed fp32x2 FMA: two output channels per instruction, scalar A broadcast
+                o2[c] = ffma2(make_float2(A[u][k].x, A[u][k].x), make_float2(W[u][8 * half + 2 * k][2 * c], W[u][8 * half + 2 * k][2 * c + 1]), o2[c]);
+                o2[c] = ffma2(make_float2(A[u][k].y, A[u][k].y), make_float2(W[u][8 * half + 2 * k + 1][2 * c], W[u][8 * half + 2 * k + 1][2 * c + 1]), o2[c]);
             }
 }
 
@@ -497,9 +498,9 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
                 s_ell[q * CB2_THREADS + threadIdx.x] = ((uint32_t)row << 12) | (uint32_t)cc[q];
             }
         }
-        float o[16];
+        float2 o2[8];
 #pragma unroll
-        for (int k = 0; k < 16; k++) o[k] = 0.f;
+        for (int k = 0; k < 8; k++) o2[k] = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             if (staged) {
@@ -525,16 +526,20 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
 #pragma unroll
                     for (int k = 0; k < 8; k++)
 #pragma unroll
-                        for (int c = 0; c < 16; c++) o[c] = fmaf(v[k], P.root[8 * half + k][c], o[c]);
+                        for (int c = 0; c < 8; c++)
+                            o2[c] = ffma2(make_float2(v[k], v[k]), make_float2(P.root[8 * half + k][2 * c], P.root[8 * half + k][2 * c + 1]), o2[c]);
                 }
 #pragma unroll 1
                 for (int grp = 0; grp < CB2_NG; grp++) {
-                    if (staged) cb2_pass<true>(N, p, n, half, grp, xa, s_rows, s_tab, s_ell, nbr, off, P, p + d1, g.ncell, o);
-                    else        cb2_pass<false>(N, p, n, half, grp, xa, s_rows, s_tab, s_ell, nbr, off, P, 0, g.ncell, o);
+                    if (staged) cb2_pass<true>(N, p, n, half, grp, xa, s_rows, s_tab, s_ell, nbr, off, P, p + d1, g.ncell, o2);
+                    else        cb2_pass<false>(N, p, n, half, grp, xa, s_rows, s_tab, s_ell, nbr, off, P, 0, g.ncell, o2);
                 }
             }
         }
         if (!active) continue;
+        float o[16];
+#pragma unroll
+        for (int c = 0; c < 8; c++) { o[2 * c] = o2[c].x; o[2 * c + 1] = o2[c].y; }
         const uint32_t w = xyb[p];
         const int x = w & 0xfff, y = (w >> 12) & 0xfff;
         const float f0 = feat_s[p], f1 = __ldg(g.posx0 + x), f2 = __ldg(g.posy0 + y);

@@ -239,7 +239,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def _grid_conv(self, geom, lv, gs: GridState, xin, pack: _ConvPack, skip, out, st):
         level = geom.levels[lv]
-        self._run("grid_conv", self.lib.dagr_grid_conv, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.mask),
+        self._run(f"grid_conv_L{lv + 1}_{pack.cin}x{pack.cout}", self.lib.dagr_grid_conv, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.mask),
                                            _lib.ptr(xin), pack.cin, pack.cout, _lib.ptr(pack.weight), _lib.ptr(pack.rootT),
                                            _lib.ptr(pack.bias), _lib.ptr(pack.scale), _lib.ptr(pack.shift),
                                            _lib.ptr(skip), 1 if pack.relu else 0, level.den_x, level.den_y,

@@ -225,7 +225,7 @@ int dagr_head_decode(const float *reg, const float *obj, const float *cls, int B
 
 /* a11 postprocess_network_output + batched_nms_coordinate_trick (model/utils.py:25-33,61-110).
  * pred f32[B,A,5+nc] (decoded, cxcywh) -> det f32[B,A,6] = (x1,y1,x2,y2,score,label) compacted in
- * descending-score order, ndet i32[B].  One CTA per image, A <= 1024. */
+ * descending-score order, ndet i32[B].  One CTA per image, A <= 256. */
 int dagr_postprocess_nms(const float *pred, int B, int A, int nc, float conf_thre, float nms_thre,
                          int width, int height, int filtering, float *det, int32_t *ndet, void *stream);
 
