@@ -45,6 +45,11 @@ class L1AParams(C.Structure):
                 ("scale", f32 * 16), ("shift", f32 * 16), ("relu", i32)]
 
 
+class L1ImgParams(C.Structure):
+    _fields_ = [("w", f32 * (KU * 24 * 16)), ("root", f32 * (24 * 16)), ("skip", f32 * (24 * 16)),
+                ("scale", f32 * 16), ("shift", f32 * 16), ("sscale", f32 * 16), ("sshift", f32 * 16), ("relu", i32)]
+
+
 class L1BParams(C.Structure):
     _fields_ = [("w", f32 * (KU * 16 * 16)), ("root", f32 * (16 * 16)), ("skip", f32 * (3 * 16)),
                 ("scale", f32 * 16), ("shift", f32 * 16), ("sscale", f32 * 16), ("sshift", f32 * 16),
@@ -59,10 +64,13 @@ _SIGS = {
     "dagr_graph_sort": (C.c_int, [C.POINTER(Geom), p, p, p, i64, p, p, p, p, p, p, p, p, p, p, p]),
     "dagr_graph_search": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, p]),
     "dagr_l1_build": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, C.POINTER(L1AParams), p, p, p, p, p, p]),
+    "dagr_l1_x0_image": (C.c_int, [C.POINTER(Geom), i64, p, p, p, C.c_int, C.c_int, p, p]),
+    "dagr_l1_conv_a_image": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, p, p]),
+    "dagr_voxel_sample_max": (C.c_int, [C.POINTER(Geom), i64, p, p, p, C.c_int, C.c_int, C.c_int, p, C.c_int, C.c_int, p]),
     "dagr_graph_export": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, p, p, i64, p]),
     "dagr_l1_conv_a": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, C.POINTER(L1AParams), p, p]),
     "dagr_l1_conv_b_pool": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, C.POINTER(L1BParams), p, p, p]),
-    "dagr_l1_conv_b_pool_voxel": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, p, p, C.POINTER(L1BParams), p, p, p, p, p, p, p]),
+    "dagr_l1_conv_b_pool_voxel": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, p, p, C.POINTER(L1BParams), p, p, p, p, p, p, p, C.c_int, p]),
     "dagr_pool1_finalize": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, C.c_int, p, p, p, p, p, p]),
     "dagr_grid_cat_pos": (C.c_int, [C.POINTER(Grid), p, p, p, C.c_int, p, p]),
     "dagr_grid_conv": (C.c_int, [C.POINTER(Grid), p, p, p, p, C.c_int, C.c_int, p, p, p, p, p, p, C.c_int, f32, f32, p, p]),

@@ -131,7 +131,7 @@ __device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, in
 __global__ void __launch_bounds__(BL_THREADS)
 k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const int2 *__restrict__ ti,
            const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
-           const __grid_constant__ dagr_l1a_params_t P, const int32_t *__restrict__ flags, int32_t *__restrict__ nbr,
+           const __grid_constant__ dagr_l1a_params_t P, const int do_conv, const int32_t *__restrict__ flags, int32_t *__restrict__ nbr,
            uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask, float *__restrict__ xa)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -362,7 +362,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
                 }
             }
         }
-        if (!active) continue;
+        if (!active || !do_conv) continue;
         // conv_a phase 2: out = sum_u W_u^T A_u + W_root^T x_i, BN, act  (weights in the constant bank)
         float o[16];
 #pragma unroll
@@ -403,7 +403,10 @@ extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *sta
                              const dagr_l1a_params_t *p_host, const int32_t *flags, int32_t *nbr, uint16_t *off,
                              uint32_t *cellmask, float *xa, void *stream)
 {
-    DAGR_CHECK_ARG(g && p_host, "null argument");
+    DAGR_CHECK_ARG(g, "null argument");
+    static const dagr_l1a_params_t zero_params = {};
+    const int do_conv = p_host != nullptr;
+    if (!p_host) p_host = &zero_params;
     DAGR_CHECK_ARG(g->K >= 1 && g->K <= DAGR_ELL, "max_neighbors must be in [1,16]");
     DAGR_CHECK_ARG(g->r >= 0 && g->r <= 15 && g->Q <= 255, "radius must be <= 15 px and max_queue_size <= 255");
     DAGR_CHECK_ARG(N < (1ll << 24), "the staged probe packs positions in 24 bits (N < 16.7M per call)");
@@ -412,7 +415,7 @@ extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *sta
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     k_l1_build<<<cells, BL_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab, *p_host,
-                                                                  flags, nbr, off, cellmask, xa);
+                                                                  do_conv, flags, nbr, off, cellmask, xa);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

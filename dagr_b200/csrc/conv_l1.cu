@@ -420,8 +420,9 @@ __global__ void __launch_bounds__(CB2_THREADS, 3)
 k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
              const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
              const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off, const float *__restrict__ tab,
-             const __grid_constant__ dagr_l1b_params_t P, float *__restrict__ x1, int32_t *__restrict__ cnt,
-             int32_t *__restrict__ pxy, float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg)
+             const __grid_constant__ dagr_l1b_params_t P, const float *__restrict__ skip_pre, float *__restrict__ x1,
+             int32_t *__restrict__ cnt, int32_t *__restrict__ pxy, float *__restrict__ tmean, float *__restrict__ tmax,
+             float *__restrict__ xg, int ldx)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ CB2Tile T;
@@ -439,7 +440,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     const int nown = p1 - p0;
     if (nown == 0) {                                                     // block-uniform
         if (threadIdx.x == 0) { cnt[cell] = 0; pxy[2 * cell] = 0; pxy[2 * cell + 1] = 0; tmean[cell] = 0.f; tmax[cell] = 0.f; }
-        if (threadIdx.x < 16) xg[(int64_t)cell * 16 + threadIdx.x] = 0.f;
+        if (threadIdx.x < 16) xg[(int64_t)cell * ldx + threadIdx.x] = 0.f;
         return;
     }
     if (threadIdx.x == 0) {
@@ -542,14 +543,25 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
         for (int c = 0; c < 8; c++) { o[2 * c] = o2[c].x; o[2 * c + 1] = o2[c].y; }
         const uint32_t w = xyb[p];
         const int x = w & 0xfff, y = (w >> 12) & 0xfff;
-        const float f0 = feat_s[p], f1 = __ldg(g.posx0 + x), f2 = __ldg(g.posy0 + y);
+        float skv[16];
+        if (skip_pre != nullptr) {
+            const float4 *sp = reinterpret_cast<const float4 *>(skip_pre + (int64_t)p * 16);
+            const float4 a = sp[0], b4 = sp[1], c4 = sp[2], d4 = sp[3];
+            skv[0] = a.x; skv[1] = a.y; skv[2] = a.z; skv[3] = a.w; skv[4] = b4.x; skv[5] = b4.y; skv[6] = b4.z; skv[7] = b4.w;
+            skv[8] = c4.x; skv[9] = c4.y; skv[10] = c4.z; skv[11] = c4.w; skv[12] = d4.x; skv[13] = d4.y; skv[14] = d4.z; skv[15] = d4.w;
+        } else {
+            const float f0 = feat_s[p], f1 = __ldg(g.posx0 + x), f2 = __ldg(g.posy0 + y);
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                float sk = f0 * P.skip[0][c];
+                sk = fmaf(f1, P.skip[1][c], sk);
+                sk = fmaf(f2, P.skip[2][c], sk);
+                skv[c] = fmaf(sk, P.sscale[c], P.sshift[c]);
+            }
+        }
 #pragma unroll
         for (int c = 0; c < 16; c++) {
-            float sk = f0 * P.skip[0][c];
-            sk = fmaf(f1, P.skip[1][c], sk);
-            sk = fmaf(f2, P.skip[2][c], sk);
-            sk = fmaf(sk, P.sscale[c], P.sshift[c]);
-            float r = fmaf(o[c], P.scale[c], P.shift[c]) + sk;
+            float r = fmaf(o[c], P.scale[c], P.shift[c]) + skv[c];
             r = P.relu ? fmaxf(r, 0.f) : r;
             o[c] = r;
             m[c] = fmaxf(m[c], r);
@@ -585,7 +597,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     if (threadIdx.x < 16) {
         float v = s_red[0][threadIdx.x];
         for (int w2 = 1; w2 < nw; w2++) v = fmaxf(v, s_red[w2][threadIdx.x]);
-        xg[(int64_t)cell * 16 + threadIdx.x] = v;
+        xg[(int64_t)cell * ldx + threadIdx.x] = v;
     }
     if (threadIdx.x == 32) {
         long long ax = 0, ay = 0, at = 0; int tmx = -2147483647;
@@ -603,8 +615,8 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
 extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
                                          const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
                                          const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
-                                         float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg,
-                                         void *stream)
+                                         const float *skip_pre, float *x1, int32_t *cnt, int32_t *pxy, float *tmean,
+                                         float *tmax, float *xg, int ldx, void *stream)
 {
     DAGR_CHECK_ARG(g && p_host, "null argument");
     const int cells = g->B * g->ny1 * g->nx1;
@@ -613,7 +625,7 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     k_l1_conv_b2<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, tab,
-                                                                     *p_host, x1, cnt, pxy, tmean, tmax, xg);
+                                                                     *p_host, skip_pre, x1, cnt, pxy, tmean, tmax, xg, ldx);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

@@ -83,7 +83,7 @@ class Engine:
         self.prof = None                     # dict name -> [(start_evt, end_evt)] when per-op timing is on
 
     # kernels enqueued by each C-ABI call (see csrc/*.cu)
-    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=1,
+    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=1, dagr_l1_x0_image=1, dagr_l1_conv_a_image=1, dagr_voxel_sample_max=1,
                      dagr_pool1_finalize=1, dagr_grid_cat_pos=1, dagr_grid_conv=1, dagr_grid_linear_bn=1, dagr_grid_pool=1,
                      dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1,
                      dagr_postprocess_nms=1, dagr_sample_features=1, dagr_denormalize_pos=1)
@@ -134,23 +134,37 @@ class Engine:
         relu = True
         l1 = bb.conv_block1
         ca, cb = l1.conv_block1, l1.conv_block2
-        if ca.conv.in_channels != 3 or ca.conv.out_channels != 16:
-            raise NotImplementedError("event-level fast path expects conv_block1 = Layer(3 -> 16) "
-                                      "(events only, base_width 0.5)")
         slots = torch.tensor(geom.slots1, dtype=torch.long)
-        pa = _lib.L1AParams()
-        _fill(pa.w, ca.conv.weight.detach().cpu()[slots])                    # [15,3,16]
-        _fill(pa.root, ca.conv.lin.weight.detach().cpu().t())               # [3,16]
-        s, b = _fold_bn(ca.norm); _fill(pa.scale, s); _fill(pa.shift, b)
-        pa.relu = 1
+        cin0 = ca.conv.in_channels
+        if ca.conv.out_channels != 16 or cin0 not in (3, 19):
+            raise NotImplementedError("event-level kernels expect conv_block1 = Layer(3 -> 16) (events only) or "
+                                      "Layer(19 -> 16) (image fusion), base_width 0.5")
         pb = _lib.L1BParams()
         _fill(pb.w, cb.conv.weight.detach().cpu()[slots])                    # [15,16,16]
         _fill(pb.root, cb.conv.lin.weight.detach().cpu().t())
-        _fill(pb.skip, cb.lin.mlp.weight.detach().cpu().t())                # [3,16]
         s, b = _fold_bn(cb.norm); _fill(pb.scale, s); _fill(pb.shift, b)
         s, b = _fold_bn(cb.norm_skip); _fill(pb.sscale, s); _fill(pb.sshift, b)
         pb.relu = 1
-        pk = dict(l1a=pa, l1b=pb)
+        pk = dict(l1b=pb, l1a=None, l1img=None)
+        if cin0 == 3:
+            pa = _lib.L1AParams()
+            _fill(pa.w, ca.conv.weight.detach().cpu()[slots])                # [15,3,16]
+            _fill(pa.root, ca.conv.lin.weight.detach().cpu().t())           # [3,16]
+            s, b = _fold_bn(ca.norm); _fill(pa.scale, s); _fill(pa.shift, b)
+            pa.relu = 1
+            _fill(pb.skip, cb.lin.mlp.weight.detach().cpu().t())            # [3,16]
+            pk["l1a"] = pa
+        else:
+            pi = _lib.L1ImgParams()
+            w = torch.zeros(15, 24, 16); w[:, :19] = ca.conv.weight.detach().cpu().float()[slots]
+            r = torch.zeros(24, 16); r[:19] = ca.conv.lin.weight.detach().cpu().float().t()
+            k = torch.zeros(24, 16); k[:19] = cb.lin.mlp.weight.detach().cpu().float().t()
+            _fill(pi.w, w); _fill(pi.root, r); _fill(pi.skip, k)
+            s, b = _fold_bn(ca.norm); _fill(pi.scale, s); _fill(pi.shift, b)
+            s, b = _fold_bn(cb.norm_skip); _fill(pi.sscale, s); _fill(pi.sshift, b)
+            pi.relu = 1
+            raw = (C.c_char * C.sizeof(pi)).from_buffer(pi)
+            pk["l1img"] = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
         pk["layers"] = [_LayerPack(getattr(bb, n), relu, device) for n in ("layer2", "layer3", "layer4", "layer5")]
         heads = []
         for k in range(hd.num_scales):
@@ -294,8 +308,26 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
+    def _append_image(self, geom, lv, gs, o, feat, ws, st, dev):
+        """sampling_skip on a voxel grid (net.py:141-142 etc.): [o | bilinear samples of `feat` at the nodes]."""
+        cells, Cc, Cf = gs.cells, o.shape[1], int(feat.shape[1])
+        xcat = self._buf(ws, f"xcat{lv}", (cells, Cc + Cf), torch.float32, dev)
+        xcat[:, :Cc] = o
+        pxy = gs.pxy[:cells].long()
+        posx = geom.d_posxr[pxy[:, 0]].contiguous()
+        posy = geom.d_posyr[pxy[:, 1]].contiguous()
+        key = ("bidx", lv)
+        if key not in ws:
+            per = geom.levels[lv].nx * geom.levels[lv].ny
+            ws[key] = (torch.arange(cells, device=dev) // per).int()
+        self._run("sample_features", self.lib.dagr_sample_features, _lib.ptr(feat), int(feat.shape[0]), Cf, int(feat.shape[2]),
+                  int(feat.shape[3]), _lib.ptr(posx), _lib.ptr(posy), _lib.ptr(ws[key]), cells, geom.W, geom.H, _lib.ptr(xcat),
+                  Cc + Cf, Cc, st)
+        return xcat
+
+    @torch.no_grad()
     def forward_events(self, batch_i32: torch.Tensor, pos_i32: torch.Tensor, feat: torch.Tensor, B: int,
-                       W: int, H: int, image_outs=None):
+                       W: int, H: int, image_feats=None, image_outs=None):
         """batch int32[N], pos int32[N,3], feat fp32[N] (polarity) on CUDA -> decoded [B, A, 5+nc]."""
         for n, t in (("batch", batch_i32), ("pos", pos_i32), ("x", feat)):
             _lib.require_cuda(t, n)
@@ -320,27 +352,45 @@ class Engine:
                                        _lib.ptr(ws["tmp"]), _lib.ptr(ws["count"]), _lib.ptr(ws["blocksums"]),
                                        _lib.ptr(ws["start"]), _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                                        _lib.ptr(ws["feat_s"]), _lib.ptr(flags), st)
-        if self.fused_build:
+        use_image = image_feats is not None
+        if use_image:
+            # adjacency only; conv_block1 runs on [polarity, 16 image samples, x, y] (net.py:117-126)
+            self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
+                      _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), None, _lib.ptr(flags), _lib.ptr(nbr), _lib.ptr(off),
+                      _lib.ptr(cellmask), _lib.ptr(ws["xa"]), st)
+            f0 = image_feats[0]
+            x0 = self._buf(ws, "x0img", (3 * max(N, 1) * 8,), torch.float32, dev)
+            skipv = self._buf(ws, "skipv", (max(N, 1), 16), torch.float32, dev)
+            self._run("l1_x0_image", lib.dagr_l1_x0_image, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(f0),
+                      int(f0.shape[2]), int(f0.shape[3]), _lib.ptr(x0), st)
+            self._run("l1_conv_a_image", lib.dagr_l1_conv_a_image, g, N, _lib.ptr(x0), _lib.ptr(nbr), _lib.ptr(off),
+                      _lib.ptr(geom.d_tab1), _lib.ptr(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), st)
+        elif self.fused_build:
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(flags), _lib.ptr(nbr), _lib.ptr(off),
                       _lib.ptr(cellmask), _lib.ptr(ws["xa"]), st)
         else:
             self._run("graph_search", lib.dagr_graph_search, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                                             _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(cellmask), st)
+                      _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(cellmask), st)
             self._run("l1_conv_a", lib.dagr_l1_conv_a, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(nbr), _lib.ptr(off),
-                                          _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(ws["xa"]), st)
+                      _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(ws["xa"]), st)
         x1 = None
         if self.keep_node_features:
             if ws["x1"] is None or ws["x1"].shape[0] < ws["cap"]:
                 ws["x1"] = torch.empty((ws["cap"], 16), dtype=torch.float32, device=dev)
             x1 = ws["x1"]
         g1: GridState = ws["grids"][0]
-        g1.x = self._buf(ws, "gx0", (g1.cells, 16), torch.float32, dev)
-        if self.voxel_conv_b:
+        c1 = 16 + (int(image_feats[1].shape[1]) if use_image else 0)
+        g1.x = self._buf(ws, "gx0", (g1.cells, c1), torch.float32, dev)
+        if self.voxel_conv_b or use_image:
             self._run("l1_conv_b_pool_voxel", lib.dagr_l1_conv_b_pool_voxel, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["ti"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]), _lib.ptr(nbr), _lib.ptr(off),
-                      _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(x1), _lib.ptr(g1.cnt), _lib.ptr(g1.pxy),
-                      _lib.ptr(g1.tmean), _lib.ptr(g1.tmax), _lib.ptr(g1.x), st)
+                      _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(skipv) if use_image else None, _lib.ptr(x1),
+                      _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean), _lib.ptr(g1.tmax), _lib.ptr(g1.x), c1, st)
+            if use_image:                                     # sampling_skip before pool1 (net.py:128-131)
+                f1 = image_feats[1]
+                self._run("voxel_sample_max", lib.dagr_voxel_sample_max, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(f1),
+                          int(f1.shape[1]), int(f1.shape[2]), int(f1.shape[3]), _lib.ptr(g1.x), c1, 16, st)
         else:
             self._run("l1_conv_b_pool", lib.dagr_l1_conv_b_pool, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]),
                       _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(x1), _lib.ptr(poolmax), st)
@@ -355,12 +405,15 @@ class Engine:
         aggr_cfg = 0 if getattr(model.args, "pooling_aggr", "max") == "max" else 1
         lay = pk["layers"]
         inter = {}
+        def cat_img(lv, gs, o, k):
+            return self._append_image(geom, lv, gs, o, image_feats[k], ws, st, dev) if use_image else o
+
         _, _, o2 = self._layer(geom, 0, g1, lay[0], ws, "layer2", st, dev)
-        g2 = self._pool(geom, 0, g1, o2, aggr_cfg, ws, st, dev, kto)
+        g2 = self._pool(geom, 0, g1, cat_img(0, g1, o2, 2), aggr_cfg, ws, st, dev, kto)
         _, _, o3 = self._layer(geom, 1, g2, lay[1], ws, "layer3", st, dev)
-        g3 = self._pool(geom, 1, g2, o3, aggr_cfg, ws, st, dev, kto)
+        g3 = self._pool(geom, 1, g2, cat_img(1, g2, o3, 3), aggr_cfg, ws, st, dev, kto)
         _, _, o4 = self._layer(geom, 2, g3, lay[2], ws, "layer4", st, dev)           # out3
-        g4 = self._pool(geom, 2, g3, o4, 1, ws, st, dev, kto)                        # pool4 is always mean (net.py:96-97)
+        g4 = self._pool(geom, 2, g3, cat_img(2, g3, o4, 4), 1, ws, st, dev, kto)     # pool4 is always mean (net.py:96-97)
         _, _, o5 = self._layer(geom, 3, g4, lay[3], ws, "layer5", st, dev)           # out4
         inter.update(o2=o2, o3=o3, o4=o4, o5=o5)
         # ---- head ----------------------------------------------------------------------------

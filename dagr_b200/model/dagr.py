@@ -166,11 +166,19 @@ class DAGR(YOLOX):
         """backbone + head up to decode_outputs: [B, n_anchors, 5 + num_classes]."""
         if not reset:
             raise NotImplementedError("incremental (reset=False) forward goes through dagr_b200.asynchronous")
-        if self.backbone.use_image:
-            raise NotImplementedError("image fusion path is not wired in this build")
         batch_i, pos_i, feat, W, H = self._prepare_events(x)
         B = int(getattr(x, "num_graphs", 0) or (int(x.batch.max()) + 1 if len(x.batch) else 1))
-        return self.engine.forward_events(batch_i, pos_i, feat, B, W, H)
+        image_feats = image_outs = None
+        if self.backbone.use_image:
+            # dense image trunk + CNN head stay torch/cuDNN (tensor cores allowed here only), net.py:110, dagr.py:205-206
+            with torch.no_grad():
+                feats, outs = self.backbone.net(x.image.float())
+                image_feats = [f.float().contiguous() for f in feats]
+                sizes = self.backbone.get_output_sizes()[-self.head.num_scales:]
+                cnn_in = [torch.nn.functional.interpolate(o, size=tuple(sz)) for o, sz in zip(outs[-self.head.num_scales:], sizes)]
+                image_outs = self.head.cnn_head(cnn_in)
+            self.last_image_outs, self.last_image_feats = image_outs, image_feats
+        return self.engine.forward_events(batch_i, pos_i, feat, B, W, H, image_feats=image_feats, image_outs=image_outs)
 
     def forward(self, x, reset=True, return_targets=True, filtering=True):
         if self.training:

@@ -97,12 +97,39 @@ int dagr_graph_search(const dagr_geom_t *g, int64_t N, const int32_t *start, con
  * polarity) records of the voxel's 3x3 neighbourhood in shared memory (three coalesced runs, thanks to the
  * cell-major order), probes the spiral entirely on chip, writes the ELL adjacency + cellmask exactly like
  * dagr_graph_search and applies conv_block1.conv_block1 (SplineConv 3->16 + BN + act, see dagr_l1_conv_a)
- * to the neighbours as they are found -> xa f32[N,16].  cellmask needs no zeroing for this entry point. */
+ * to the neighbours as they are found -> xa (half-major [2][N][8]).  cellmask needs no zeroing for this
+ * entry point.  With p_host == NULL only the adjacency / cellmask are produced (image path). */
 struct dagr_l1a_params_s;
 int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
                   const uint32_t *xyb, const float *feat_s, const float *tab,
                   const struct dagr_l1a_params_s *p_host, const int32_t *flags /* from dagr_graph_sort, or NULL */,
                   int32_t *nbr, uint16_t *off, uint32_t *cellmask, float *xa, void *stream);
+
+/* ---- image fusion at the event level (use_image, net.py:117-131): conv_block1 = Layer(1+16+2 -> 16) ----
+ * x0 f32[3][N][8] chunk-major = [polarity, 16 bilinear samples of image_feat[0] at the event, x/W, y/H, pad];
+ * sampling follows net.py:193-221 (grid_sample, align_corners=True, batch as depth). */
+int dagr_l1_x0_image(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, const float *feat_s,
+                     const float *img0 /*[B,16,h,w]*/, int h, int w, float *x0, void *stream);
+
+typedef struct {
+    float w[DAGR_KU][24][16];     /* slot-major spline weights, input channels padded 19 -> 24 */
+    float root[24][16];
+    float skip[24][16];           /* ConvBlockWithSkip.lin of conv_block2 (applied to the layer input x0) */
+    float scale[16], shift[16];   /* conv_block1.norm  */
+    float sscale[16], sshift[16]; /* conv_block2.norm_skip */
+    int32_t relu;
+} dagr_l1img_params_t;
+
+/* conv_block1.conv_block1 on 19 input channels -> xa (half-major [2][N][8]) and the layer's skip branch
+ * skipv f32[N,16] = BN(Linear(x0)) consumed by dagr_l1_conv_b_pool_voxel(skip_pre) */
+int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const float *x0, const int32_t *nbr, const uint16_t *off,
+                         const float *tab, const dagr_l1img_params_t *p_dev /* DEVICE copy (26 KB) */, float *xa, float *skipv,
+                         void *stream);
+
+/* per-voxel channel max of image features sampled at the voxel's events (sampling_skip before pool1,
+ * net.py:128-131): xg[cell*ldx + c0 + c], c < C, empty voxels -> 0 */
+int dagr_voxel_sample_max(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
+                          const float *img /*[B,C,h,w]*/, int C, int h, int w, float *xg, int ldx, int c0, void *stream);
 
 int dagr_graph_export(const dagr_geom_t *g, int64_t N, const int32_t *perm, const int32_t *ti,
                       const int32_t *nbr, int32_t *inv, int32_t *rowptr, int32_t *blocksums,
@@ -150,8 +177,9 @@ int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, co
 int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
                               const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
                               const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
+                              const float *skip_pre /* f32[N,16] or NULL: precomputed skip branch (image path) */,
                               float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg,
-                              void *stream);
+                              int ldx /* row stride of xg (>= 16) */, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Coarse levels live on dense voxel grids [B, ny, nx]: per cell  valid, pixel position, features,

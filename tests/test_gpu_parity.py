@@ -243,13 +243,15 @@ def test_forward_parity_vs_oracle(W, H, B, n, kind, size, dataset):
         assert len(nodes["cell"]) == pl["x"].shape[0], f"level {lv}: node count"
         assert torch.equal(nodes["batch"].cpu(), pl["batch"]), f"level {lv}: batch"
         amb = pl["ambiguous"]
-        assert torch.equal(nodes["pos"].cpu()[~amb], pl["pos"][:, :2][~amb]), f"level {lv}: rounded positions"
+        same = nodes["pos"].cpu() == pl["pos"][:, :2]
+        assert bool(same[~amb].all()), f"level {lv}: rounded positions"
         e = export.grid_edges(gs, level).cpu()
-        if not bool(amb.any()):
-            assert torch.equal(e, pl["edge_index"]), f"level {lv}: coarse edge_index"
+        assert torch.equal(e, pl["edge_index"]), f"level {lv}: coarse edge_index"
         assert_close(nodes["x"].cpu(), pl["x"], what=f"level {lv} pooled features")
-        if bool(amb.any()):
-            pytest.skip("ambiguous pooled position (oracle mask): deeper levels not comparable")
+        if not bool(same.all()):
+            # the oracle itself flags these voxels: their mean position is within float noise of a pixel boundary
+            # (the reference's atomic fp32 mean is not run-to-run stable there)
+            pytest.skip("pooled position differs only at oracle-flagged ambiguous voxels: deeper levels not comparable")
     assert_close(L["inter"]["o4"][L["grids"][2].cnt[:L["grids"][2].cells] > 0].cpu(), o["out3"], what="out3")
     assert_close(L["inter"]["o5"][L["grids"][3].cnt[:L["grids"][3].cells] > 0].cpu(), o["out4"], what="out4")
     for k, d in enumerate(L["dense"]):
@@ -267,6 +269,42 @@ def test_forward_parity_vs_oracle(W, H, B, n, kind, size, dataset):
             assert torch.equal(dets[b]["labels"].cpu(), rb["labels"])
             assert_close(dets[b]["boxes"].cpu(), rb["boxes"], what="boxes")
             assert_close(dets[b]["scores"].cpu(), rb["scores"], what="scores")
+
+
+@pytest.mark.parametrize("W,H,B,n,size", [(240, 180, 2, 5000, "n"), (320, 215, 1, 9000, "s")])
+def test_image_fusion_parity_vs_oracle(W, H, B, n, size):
+    """use_image: sampled ResNet features enter every Layer input and every pooling, CNN head maps are added to the
+    dense outputs.  The dense trunk is torch/cuDNN on both sides (its tensors are handed to the oracle)."""
+    from dagr_b200 import export
+    from dagr_b200.data import format_data, synth_batch
+    from oracle.ref_model import RefModel
+    model, args = make_model(size, H, W, use_image=True, img_net="resnet18")
+    model.cuda()
+    raw = synth_batch(B, n, W, H, seed=77, kind="clustered", with_image=True, ragged=True)
+    data = format_data(raw.clone())
+    d = data.clone().cuda()
+    model.engine.keep_node_features = True
+    dec = model.forward_decoded(d)
+    torch.cuda.synchronize()
+    L = model.engine.last
+    feats = [f.cpu() for f in model.last_image_feats]
+    outs = {k: [t.cpu() for t in v] for k, v in model.last_image_outs.items()}
+    ref = RefModel({k: v.cpu() for k, v in model.state_dict().items()}, args, H, W)
+    o = ref.forward(data.x, data.pos, data.batch, B, image_feats=feats, image_outs=outs)
+    assert torch.equal(model.engine.export_edges().cpu(), o["edge_index"])
+    N = L["N"]
+    assert_close(export.unsort_rows(model.engine.xa_rows(), L["ws"]["perm"], N).cpu(), o["x1a"], what="conv_block1.conv_block1 (image)")
+    assert_close(export.unsort_rows(L["x1"], L["ws"]["perm"], N).cpu(), o["x1"], what="conv_block1 (image)")
+    geom = L["geom"]
+    for lv in range(4):
+        pl = o["levels"][lv]
+        nodes = export.grid_nodes(L["grids"][lv], geom.levels[lv], geom)
+        same = nodes["pos"].cpu() == pl["pos"][:, :2]
+        assert bool(same[~pl["ambiguous"]].all())
+        assert_close(nodes["x"].cpu(), pl["x"], what=f"level {lv} pooled features (image)")
+        if not bool(same.all()):
+            pytest.skip("pooled position differs only at oracle-flagged ambiguous voxels")
+    assert_close(dec.cpu(), o["decoded"], what="decoded outputs (image)")
 
 
 def test_batch_independence_and_full_size_properties():
