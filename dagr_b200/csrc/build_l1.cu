@@ -20,6 +20,7 @@ struct BLTile {
     int run_start[3], run_off[3], run_len[3];
     int smin, smax;              // slice (t / delta_t) range of the voxel's own events
     int unsorted;                // some pixel's records are not time-sorted -> no time bucketing
+    int maxidx;                  // newest arrival index among the events this launch must process (-1: none)
 };
 
 __host__ __device__ __forceinline__ size_t bl_acc_offset(const dagr_geom_t &g)
@@ -131,7 +132,8 @@ __device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, in
 __global__ void __launch_bounds__(BL_THREADS)
 k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const int2 *__restrict__ ti,
            const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
-           const __grid_constant__ dagr_l1a_params_t P, const int do_conv, const int32_t *__restrict__ flags, int32_t *__restrict__ nbr,
+           const __grid_constant__ dagr_l1a_params_t P, const int do_conv, const int min_idx, const int32_t *__restrict__ flags,
+           int32_t *__restrict__ nbr,
            uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask, float *__restrict__ xa)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -141,7 +143,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
     const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
-    if (p1 == p0) { if (threadIdx.x == 0) cellmask[cell] = 0; return; }      // block-uniform
+    if (p1 == p0) { if (threadIdx.x == 0 && min_idx <= 0) cellmask[cell] = 0; return; }      // block-uniform
 
     // ---- shared memory carve-up -------------------------------------------------------------------
     const int TWmax = g.CW + 2 * g.r, THmax = g.CH + 2 * g.r, TPmax = TWmax * THmax;
@@ -172,7 +174,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
             T.run_start[rr] = s; T.run_len[rr] = e - s; T.run_off[rr] = o;
             o += e - s;
         }
-        T.smin = 0x7fffffff; T.smax = -0x7fffffff; T.unsorted = 0;
+        T.smin = 0x7fffffff; T.smax = -0x7fffffff; T.unsorted = 0; T.maxidx = -1;
         s_mask = 0;
     }
     __syncthreads();
@@ -228,12 +230,17 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     }
     // slice range of the voxel's own events
     {
-        int mn = 0x7fffffff, mx = -0x7fffffff;
-        for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) { const int sl = ti[p].x / dtw; mn = min(mn, sl); mx = max(mx, sl); }
-        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
-        if ((threadIdx.x & 31) == 0) { atomicMin(&T.smin, mn); atomicMax(&T.smax, mx); }
+        int mn = 0x7fffffff, mx = -0x7fffffff, mi = -1;
+        for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+            const int2 r = ti[p];
+            if (r.y < min_idx) continue;                                // incremental mode: only new events are processed
+            const int sl = r.x / dtw; mn = min(mn, sl); mx = max(mx, sl); mi = max(mi, r.y);
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx); mi = __reduce_max_sync(0xffffffffu, mi);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&T.smin, mn); atomicMax(&T.smax, mx); atomicMax(&T.maxidx, mi); }
     }
     __syncthreads();
+    if (T.maxidx < 0) return;                                           // block-uniform: no new event in this voxel
     // ---- per-pixel time-bucket ranges ---------------------------------------------------------------
     // bucket(t) = clamp(t/delta_t - (smin-1), 0, NB-1); an event in bucket e needs records of buckets {e-1, e}.
     const int sbase = T.smin - 1;
@@ -291,7 +298,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         // (unsaturated, slow) events of the voxel, so no warp is the straggler of the CTA
         const int nw = blockDim.x >> 5;
         const int rank = (int)(threadIdx.x & 31) * nw + (int)(threadIdx.x >> 5);
-        const bool active = rank < chunk;
+        bool active = rank < chunk;
         const int p = p0 + pb0 + (active ? (int)s_order[rank] : 0);
         int x = 0, y = 0;
         int2 me = make_int2(0, 0);
@@ -299,6 +306,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
             const uint32_t w = xyb[p];
             x = w & 0xfff; y = (w >> 12) & 0xfff;
             me = ti[p];
+            active = me.y >= min_idx;
         }
         const int tx0 = active ? x - T.X0 : g.r, ty0 = active ? y - T.Y0 : g.r;
         int eb = 0;
@@ -393,14 +401,14 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     mloc = __reduce_or_sync(0xffffffffu, mloc);
     if ((threadIdx.x & 31) == 0 && mloc) atomicOr(&s_mask, mloc);
     __syncthreads();
-    if (threadIdx.x == 0) cellmask[cell] = s_mask;
+    if (threadIdx.x == 0) cellmask[cell] = (min_idx > 0 ? cellmask[cell] : 0u) | s_mask;
 }
 
 
 
 extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
                              const uint32_t *xyb, const float *feat_s, const float *tab,
-                             const dagr_l1a_params_t *p_host, const int32_t *flags, int32_t *nbr, uint16_t *off,
+                             const dagr_l1a_params_t *p_host, const int32_t *flags, int min_idx, int32_t *nbr, uint16_t *off,
                              uint32_t *cellmask, float *xa, void *stream)
 {
     DAGR_CHECK_ARG(g, "null argument");
@@ -415,7 +423,7 @@ extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *sta
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     k_l1_build<<<cells, BL_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab, *p_host,
-                                                                  do_conv, flags, nbr, off, cellmask, xa);
+                                                                  do_conv, min_idx, flags, nbr, off, cellmask, xa);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

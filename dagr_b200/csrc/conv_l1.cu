@@ -420,9 +420,9 @@ __global__ void __launch_bounds__(CB2_THREADS, 3)
 k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
              const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
              const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off, const float *__restrict__ tab,
-             const __grid_constant__ dagr_l1b_params_t P, const float *__restrict__ skip_pre, float *__restrict__ x1,
-             int32_t *__restrict__ cnt, int32_t *__restrict__ pxy, float *__restrict__ tmean, float *__restrict__ tmax,
-             float *__restrict__ xg, int ldx)
+             const __grid_constant__ dagr_l1b_params_t P, const float *__restrict__ skip_pre, const int min_idx,
+             float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
+             float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ CB2Tile T;
@@ -482,7 +482,12 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     uint32_t parity = 0;
     for (int pb0 = p0; pb0 < p1; pb0 += blockDim.x) {
         const int p = pb0 + threadIdx.x;
-        const bool active = p < p1;
+        const bool inrange = p < p1;
+        const int2 rec = inrange ? ti[p] : make_int2(0, 0);
+        const uint32_t wxy = inrange ? xyb[p] : 0u;
+        if (inrange) { sx += wxy & 0xfff; sy += (wxy >> 12) & 0xfff; st += rec.x; tm = max(tm, rec.x); }
+        const bool active = inrange && rec.y >= min_idx;                 // incremental mode: only new nodes are convolved
+        if (!__syncthreads_or(active)) continue;                         // block-uniform: nothing to do in this chunk
         const int n = active ? nbr[(int64_t)(DAGR_ELL - 1) * N + p] : 0;
         // stage this node's ELL row (independent loads -> one global latency); neighbour positions become staged rows
         if (staged && active) {
@@ -541,8 +546,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
         float o[16];
 #pragma unroll
         for (int c = 0; c < 8; c++) { o[2 * c] = o2[c].x; o[2 * c + 1] = o2[c].y; }
-        const uint32_t w = xyb[p];
-        const int x = w & 0xfff, y = (w >> 12) & 0xfff;
+        const int x = wxy & 0xfff, y = (wxy >> 12) & 0xfff;
         float skv[16];
         if (skip_pre != nullptr) {
             const float4 *sp = reinterpret_cast<const float4 *>(skip_pre + (int64_t)p * 16);
@@ -573,8 +577,6 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             dst[2] = make_float4(o[8], o[9], o[10], o[11]);
             dst[3] = make_float4(o[12], o[13], o[14], o[15]);
         }
-        const int t = ti[p].x;
-        sx += x; sy += y; st += t; tm = max(tm, t);
     }
     // ---- pool1: per-voxel max / mean position (pooling.py:66-86) -------------------------------------
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -597,6 +599,10 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     if (threadIdx.x < 16) {
         float v = s_red[0][threadIdx.x];
         for (int w2 = 1; w2 < nw; w2++) v = fmaxf(v, s_red[w2][threadIdx.x]);
+        if (persist != nullptr) {                                        // running per-voxel max of the stream
+            if (min_idx > 0) v = fmaxf(v, persist[(int64_t)cell * 16 + threadIdx.x]);
+            persist[(int64_t)cell * 16 + threadIdx.x] = v;
+        }
         xg[(int64_t)cell * ldx + threadIdx.x] = v;
     }
     if (threadIdx.x == 32) {
@@ -615,8 +621,8 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
 extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
                                          const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
                                          const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
-                                         const float *skip_pre, float *x1, int32_t *cnt, int32_t *pxy, float *tmean,
-                                         float *tmax, float *xg, int ldx, void *stream)
+                                         const float *skip_pre, int min_idx, float *persist, float *x1, int32_t *cnt,
+                                         int32_t *pxy, float *tmean, float *tmax, float *xg, int ldx, void *stream)
 {
     DAGR_CHECK_ARG(g && p_host, "null argument");
     const int cells = g->B * g->ny1 * g->nx1;
@@ -625,7 +631,35 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     k_l1_conv_b2<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, tab,
-                                                                     *p_host, skip_pre, x1, cnt, pxy, tmean, tmax, xg, ldx);
+                                                                     *p_host, skip_pre, min_idx, persist, x1, cnt, pxy, tmean, tmax, xg, ldx);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// streaming support: node rows live in arrival order between steps (the cell-major order changes whenever
+// events are appended); gather old rows into the new sorted order / scatter freshly computed rows back.
+// xa_sorted is half-major [2][N][8]; xa_arrival is row-major [cap][16].
+// ------------------------------------------------------------------------------------------------
+__global__ void k_xa_permute(int64_t N, const int32_t *__restrict__ perm, int n_old, float *__restrict__ xa_sorted,
+                             float *__restrict__ xa_arrival, int scatter)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = t >> 2;
+    const int q = (int)(t & 3);
+    if (p >= N) return;
+    const int i = perm[p];
+    float4 *srt = reinterpret_cast<float4 *>(xa_sorted + ((int64_t)(q >> 1) * N + p) * 8) + (q & 1);
+    float4 *arr = reinterpret_cast<float4 *>(xa_arrival + (int64_t)i * 16) + q;
+    if (scatter) { if (i >= n_old) *arr = *srt; }
+    else         { if (i < n_old) *srt = *arr; }
+}
+
+extern "C" int dagr_xa_permute(int64_t N, const int32_t *perm, int n_old, float *xa_sorted, float *xa_arrival, int scatter, void *stream)
+{
+    if (N <= 0) return DAGR_OK;
+    k_xa_permute<<<dagr_div_up(4 * N, 256), 256, 0, (cudaStream_t)stream>>>(N, perm, n_old, xa_sorted, xa_arrival, scatter);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

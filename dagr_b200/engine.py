@@ -83,7 +83,7 @@ class Engine:
         self.prof = None                     # dict name -> [(start_evt, end_evt)] when per-op timing is on
 
     # kernels enqueued by each C-ABI call (see csrc/*.cu)
-    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=1, dagr_l1_x0_image=1, dagr_l1_conv_a_image=1, dagr_voxel_sample_max=1,
+    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=1, dagr_l1_x0_image=1, dagr_xa_permute=1, dagr_l1_conv_a_image=1, dagr_voxel_sample_max=1,
                      dagr_pool1_finalize=1, dagr_grid_cat_pos=1, dagr_grid_conv=1, dagr_grid_linear_bn=1, dagr_grid_pool=1,
                      dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1,
                      dagr_postprocess_nms=1, dagr_sample_features=1, dagr_denormalize_pos=1)
@@ -327,7 +327,7 @@ class Engine:
 
     @torch.no_grad()
     def forward_events(self, batch_i32: torch.Tensor, pos_i32: torch.Tensor, feat: torch.Tensor, B: int,
-                       W: int, H: int, image_feats=None, image_outs=None):
+                       W: int, H: int, image_feats=None, image_outs=None, stream_state=None, n_old: int = 0):
         """batch int32[N], pos int32[N,3], feat fp32[N] (polarity) on CUDA -> decoded [B, A, 5+nc]."""
         for n, t in (("batch", batch_i32), ("pos", pos_i32), ("x", feat)):
             _lib.require_cuda(t, n)
@@ -345,6 +345,14 @@ class Engine:
         ws["zero_buf"].zero_()
         nbr, off = ws["nbr"], ws["off"]
         cellmask = self._zs(ws, "cellmask", torch.int32)
+        min_idx, persist = 0, None
+        if stream_state is not None:
+            # incremental step: the first n_old arrival indices were processed before; only newer events get
+            # their edges / activations computed (the causal graph never changes an old node's inputs)
+            if image_feats is not None:
+                raise NotImplementedError("streaming updates are implemented for the events-only model")
+            stream_state.ensure(geom, N, dev)
+            cellmask, persist, min_idx = stream_state.cellmask, stream_state.voxmax, int(n_old)
         poolmax = self._zs(ws, "poolmax", torch.int32)
         flags = self._zs(ws, "flags", torch.int32)
         # ---- event level ---------------------------------------------------------------------
@@ -356,7 +364,7 @@ class Engine:
         if use_image:
             # adjacency only; conv_block1 runs on [polarity, 16 image samples, x, y] (net.py:117-126)
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                      _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), None, _lib.ptr(flags), _lib.ptr(nbr), _lib.ptr(off),
+                      _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), None, _lib.ptr(flags), 0, _lib.ptr(nbr), _lib.ptr(off),
                       _lib.ptr(cellmask), _lib.ptr(ws["xa"]), st)
             f0 = image_feats[0]
             x0 = self._buf(ws, "x0img", (3 * max(N, 1) * 8,), torch.float32, dev)
@@ -365,10 +373,16 @@ class Engine:
                       int(f0.shape[2]), int(f0.shape[3]), _lib.ptr(x0), st)
             self._run("l1_conv_a_image", lib.dagr_l1_conv_a_image, g, N, _lib.ptr(x0), _lib.ptr(nbr), _lib.ptr(off),
                       _lib.ptr(geom.d_tab1), _lib.ptr(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), st)
-        elif self.fused_build:
+        elif self.fused_build or stream_state is not None:
+            if min_idx > 0:
+                self._run("xa_gather", lib.dagr_xa_permute, N, _lib.ptr(ws["perm"]), min_idx, _lib.ptr(ws["xa"]),
+                          _lib.ptr(stream_state.xa_arr), 0, st)
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                      _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(flags), _lib.ptr(nbr), _lib.ptr(off),
-                      _lib.ptr(cellmask), _lib.ptr(ws["xa"]), st)
+                      _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(flags), min_idx, _lib.ptr(nbr),
+                      _lib.ptr(off), _lib.ptr(cellmask), _lib.ptr(ws["xa"]), st)
+            if stream_state is not None:
+                self._run("xa_scatter", lib.dagr_xa_permute, N, _lib.ptr(ws["perm"]), min_idx, _lib.ptr(ws["xa"]),
+                          _lib.ptr(stream_state.xa_arr), 1, st)
         else:
             self._run("graph_search", lib.dagr_graph_search, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(cellmask), st)
@@ -382,11 +396,11 @@ class Engine:
         g1: GridState = ws["grids"][0]
         c1 = 16 + (int(image_feats[1].shape[1]) if use_image else 0)
         g1.x = self._buf(ws, "gx0", (g1.cells, c1), torch.float32, dev)
-        if self.voxel_conv_b or use_image:
+        if self.voxel_conv_b or use_image or stream_state is not None:
             self._run("l1_conv_b_pool_voxel", lib.dagr_l1_conv_b_pool_voxel, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["ti"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]), _lib.ptr(nbr), _lib.ptr(off),
-                      _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(skipv) if use_image else None, _lib.ptr(x1),
-                      _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean), _lib.ptr(g1.tmax), _lib.ptr(g1.x), c1, st)
+                      _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(skipv) if use_image else None, min_idx, _lib.ptr(persist),
+                      _lib.ptr(x1), _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean), _lib.ptr(g1.tmax), _lib.ptr(g1.x), c1, st)
             if use_image:                                     # sampling_skip before pool1 (net.py:128-131)
                 f1 = image_feats[1]
                 self._run("voxel_sample_max", lib.dagr_voxel_sample_max, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(f1),

@@ -91,6 +91,8 @@ class DAGR(YOLOX):
         self.args = args
         self.time_window = int(getattr(args, "time_window_us", 1000000))
         self._engine = None
+        self._async = None
+        self.keep_stream = False        # True: forward(reset=True) starts a stream that forward(reset=False) extends
         if "img_net_checkpoint" in args:
             sd = torch.load(args.img_net_checkpoint, map_location="cpu")["ema"]
             for name in ("backbone.net.", "head.cnn_head."):
@@ -106,12 +108,13 @@ class DAGR(YOLOX):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k == "_engine" else copy.deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_engine", "_async") else copy.deepcopy(v, memo)
         return new
 
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_engine"] = None
+        d["_async"] = None
         return d
 
     @property
@@ -165,7 +168,16 @@ class DAGR(YOLOX):
     def forward_decoded(self, x, reset=True):
         """backbone + head up to decode_outputs: [B, n_anchors, 5 + num_classes]."""
         if not reset:
-            raise NotImplementedError("incremental (reset=False) forward goes through dagr_b200.asynchronous")
+            # incremental call sequence of the reference (evaluate_flops.py:115-116: forward(reset=True) then
+            # forward(new events, reset=False)): append to the stream started by the last reset=True forward
+            if self._async is None:
+                raise RuntimeError("forward(reset=False) must follow a forward(reset=True, ...) made with keep_stream=True "
+                                   "or use dagr_b200.asynchronous.AsyncDAGR directly")
+            return self._async.step_decoded(x, batch_size=int(getattr(x, "num_graphs", 1) or 1))
+        if self.keep_stream:
+            from ..asynchronous import AsyncDAGR
+            self._async = AsyncDAGR(self)
+            return self._async.step_decoded(x, batch_size=int(getattr(x, "num_graphs", 1) or 1))
         batch_i, pos_i, feat, W, H = self._prepare_events(x)
         B = int(getattr(x, "num_graphs", 0) or (int(x.batch.max()) + 1 if len(x.batch) else 1))
         image_feats = image_outs = None

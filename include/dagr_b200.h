@@ -103,7 +103,13 @@ struct dagr_l1a_params_s;
 int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
                   const uint32_t *xyb, const float *feat_s, const float *tab,
                   const struct dagr_l1a_params_s *p_host, const int32_t *flags /* from dagr_graph_sort, or NULL */,
+                  int min_idx /* incremental mode: only events with arrival idx >= min_idx are processed and cellmask is
+                                 OR-ed into its previous content; 0 = everything */,
                   int32_t *nbr, uint16_t *off, uint32_t *cellmask, float *xa, void *stream);
+
+/* streaming (a13): node rows live in arrival order between steps; gather (scatter=0: rows of nodes < n_old into the
+ * new sorted order) / scatter (scatter=1: rows of nodes >= n_old back).  xa_sorted [2][N][8], xa_arrival [cap][16]. */
+int dagr_xa_permute(int64_t N, const int32_t *perm, int n_old, float *xa_sorted, float *xa_arrival, int scatter, void *stream);
 
 /* ---- image fusion at the event level (use_image, net.py:117-131): conv_block1 = Layer(1+16+2 -> 16) ----
  * x0 f32[3][N][8] chunk-major = [polarity, 16 bilinear samples of image_feat[0] at the event, x/W, y/H, pad];
@@ -178,6 +184,8 @@ int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *st
                               const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
                               const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
                               const float *skip_pre /* f32[N,16] or NULL: precomputed skip branch (image path) */,
+                              int min_idx /* incremental mode: only nodes with arrival idx >= min_idx are convolved */,
+                              float *persist /* f32[cells,16] or NULL: running per-voxel max across streaming steps */,
                               float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg,
                               int ldx /* row stride of xg (>= 16) */, void *stream);
 

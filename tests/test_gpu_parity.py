@@ -307,6 +307,59 @@ def test_image_fusion_parity_vs_oracle(W, H, B, n, size):
     assert_close(dec.cpu(), o["decoded"], what="decoded outputs (image)")
 
 
+@pytest.mark.parametrize("W,H,B,n,chunks", [(240, 180, 1, 8000, [7999, 1]), (640, 480, 2, 30000, [0.5, 0.2, 0.2, 0.1])])
+def test_async_incremental_equals_dense(W, H, B, n, chunks):
+    """the reference's own invariant (evaluate_flops.py:90,139-147): init on N-1 events + 1-event update == dense
+    forward on N events; generalised to several chunks and to B > 1 (tolerance 1e-5 instead of 1e-3)."""
+    from dagr_b200.asynchronous import AsyncDAGR
+    from dagr_b200.data import EventBatch
+    from dagr_b200 import export
+    model, args = make_model("n", H, W)
+    model.cuda()
+    raw, data = make_inputs(B, n, W, H, seed=5, kind="clustered")
+    dense, _, _ = _run_graph(model, data, B)
+    dense = dense.clone()
+    g_dense = [export.grid_nodes(model.engine.last["grids"][lv], model.engine.last["geom"].levels[lv], model.engine.last["geom"]) for lv in range(2)]
+    g_dense = [dict(x=g["x"].clone(), pos=g["pos"].clone(), cell=g["cell"].clone()) for g in g_dense]
+    e_dense = export.grid_edges(model.engine.last["grids"][0], model.engine.last["geom"].levels[0]).clone()
+
+    # split every sample's (time-sorted) events into the same fractions
+    per_sample = [torch.nonzero(data.batch == b).flatten() for b in range(B)]
+    bounds = []
+    for idx in per_sample:
+        if isinstance(chunks[0], float):
+            cuts = (torch.tensor([0.0] + list(chunks)).cumsum(0) * len(idx)).long()
+            cuts[-1] = len(idx)
+        else:
+            cuts = torch.tensor([0] + list(chunks)).cumsum(0).clamp(max=len(idx))
+            cuts[-1] = len(idx)
+        bounds.append(cuts)
+    a = AsyncDAGR(model)
+    dec = None
+    for c in range(len(chunks)):
+        sel = torch.cat([per_sample[b][bounds[b][c]:bounds[b][c + 1]] for b in range(B)])
+        chunk = EventBatch(x=data.x[sel], pos=data.pos[sel], batch=data.batch[sel], width=data.width, height=data.height,
+                           time_window=data.time_window, num_graphs=B)
+        dec = a.step_decoded(chunk.cuda(), batch_size=B)
+    torch.cuda.synchronize()
+    L = model.engine.last
+    for lv in range(2):
+        g = export.grid_nodes(L["grids"][lv], L["geom"].levels[lv], L["geom"])
+        assert torch.equal(g["cell"], g_dense[lv]["cell"]) and torch.equal(g["pos"], g_dense[lv]["pos"])
+        assert_close(g["x"], g_dense[lv]["x"], tol=1e-5, what=f"async level {lv} features")
+    assert torch.equal(export.grid_edges(L["grids"][0], L["geom"].levels[0]), e_dense)
+    assert_close(dec, dense, tol=1e-5, what="async decoded vs dense")
+    # sliding window: evict the oldest 20 ms and compare with the dense forward on the live window
+    t_cut = 970000
+    dec_live = a.evict_older_than(t_cut).clone()
+    keep = (model._prepare_events(data.clone().cuda())[1][:, 2] >= t_cut).cpu()
+    live = EventBatch(x=data.x[keep], pos=data.pos[keep], batch=data.batch[keep], width=data.width, height=data.height,
+                      time_window=data.time_window, num_graphs=B)
+    dense_live, _, _ = _run_graph(model, live, B)
+    assert a.num_events == int(keep.sum())
+    assert_close(dec_live, dense_live, tol=1e-5, what="live window after eviction vs dense")
+
+
 def test_batch_independence_and_full_size_properties():
     """config-2 shape (640x480, B=8, 300k events/sample): size-independent properties."""
     W, H, B, n = 640, 480, 8, 300000
