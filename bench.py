@@ -286,10 +286,10 @@ def main():
     # algorithmic bytes of the fused conv_b (+skip, +pool1 max) launch: SURVEY 8(d)
     #   x_in 64 + x_out 64 + skip input 12 + rowptr 4 per event, 8 per edge
     cb_bytes = N * (64 + 64 + 12 + 4) + 8 * E
-    cb_ms = prof.get("l1_conv_b_pool", dict(ms=float("nan")))["ms"]
+    cb_ms = (prof.get("l1_conv_b_pool_voxel") or prof.get("l1_conv_b_pool") or dict(ms=float("nan")))["ms"]
     ach = cb_bytes / (cb_ms * 1e-3) / 1e9
     cb_flops = 2.0 * (E * 15 * 16 + N * (15 * 256 + 256 + 48))          # slot form actually executed
-    roofline = dict(kernel="k_l1_conv_b (fused SplineConv 16->16 + BN + skip + act + pool1 max)", bound="hbm",
+    roofline = dict(kernel="k_l1_conv_b2 (fused SplineConv 16->16 + BN + skip + act + pool1 max/mean/round, TMA-staged, one CTA per voxel)", bound="hbm",
                     achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
                     algorithmic_bytes_per_launch=cb_bytes, launch_ms=cb_ms, share_of_step=cb_ms / tot_ms,
                     fp32_tflops=cb_flops / (cb_ms * 1e-3) / 1e12, mean_degree=E / max(N, 1),

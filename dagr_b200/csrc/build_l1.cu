@@ -29,7 +29,11 @@ __host__ __device__ __forceinline__ size_t bl_acc_offset(const dagr_geom_t &g)
     const size_t o = (size_t)BL_CAP * 12 + TP * 4 + (TW + TH) * 4 + TP * BL_NB * 2 + (size_t)g.ncell * 4 + BL_THREADS * 2 + (TW + TH);
     return (o + 15) / 16 * 16;
 }
-static size_t bl_smem_bytes(const dagr_geom_t *g) { return bl_acc_offset(*g) + (size_t)(DAGR_ELL - 1) * BL_THREADS * 4 + 16; }
+static size_t bl_smem_bytes(const dagr_geom_t *g)
+{
+    const size_t TW = g->CW + 2 * g->r, TH = g->CH + 2 * g->r;
+    return bl_acc_offset(*g) + (size_t)(DAGR_ELL - 1) * BL_THREADS * 4 + (size_t)BL_NB * (TW + TH) * 4 + 16;
+}
 
 #define BL_R1 96                 // spiral cells walked one-thread-per-event before unsaturated events are handed
                                  // to the warp-cooperative continuation (saturated events need ~85 cells)
@@ -80,6 +84,72 @@ __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p,
                     }
                 }
             }
+        }
+    }
+    n_out = active ? n : 0;
+}
+
+// Ring walk with occupancy bitmasks.  For every time bucket e the CTA keeps, per tile row, a 32-bit mask of the
+// pixels whose bucket range is non-empty (and the transposed per-column masks).  Ring d of the spiral consists of
+// four straight segments (spiral.h: right column upwards, top row leftwards, left column downwards, bottom row
+// rightwards, 2d cells each), so the candidate cells of a segment are one bit-field extract (+ a bit reversal
+// for the two descending legs).  Each lane then visits ONLY its non-empty cells, in spiral order, by clearing
+// the lowest set bit: empty pixels (~2/3 of the window) cost nothing and lanes are no longer held to the
+// warp-wide maximum of per-cell work.  Unsaturated events simply run out of rings (no second phase needed).
+template <bool STAGED>
+__device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, int p, bool active, const int2 me, int eb, int tx0, int ty0,
+                                               int TW, int TH, const uint32_t *s_pbin, const uint16_t *s_rng, const uint32_t *s_occ_r,
+                                               const uint32_t *s_occ_c, const int2 *s_ti, const int2 *__restrict__ ti, uint32_t *s_acc,
+                                               int32_t *__restrict__ nbr, uint16_t *__restrict__ off, int &n_out)
+{
+    const int kmax = g.K - 1;
+    int n = active ? 0 : kmax;
+    const uint32_t *occr = s_occ_r + eb * TH, *occc = s_occ_c + eb * TW;
+    auto visit = [&](int pix, int c) {
+        const uint32_t rg = s_rng[pix * BL_NB + eb];
+        const int lo = rg & 0xff, hi = rg >> 8;
+        const int base = (int)(s_pbin[pix] >> 8);
+        for (int j = base + hi - 1; j >= base + lo && n < kmax; j--) {     // FIFO order: newest first
+            const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
+            if (o.y < me.y && me.x - o.x <= g.dt_us) {                      // ev_graph.cu:64-69
+                if (STAGED) s_acc[n * BL_THREADS + threadIdx.x] = ((uint32_t)j << 10) | (uint32_t)c;
+                else { nbr[(int64_t)n * N + p] = j; off[(int64_t)n * N + p] = (uint16_t)c; }
+                n++;
+            }
+        }
+    };
+    if (n < kmax && ((occr[ty0] >> tx0) & 1u)) visit(ty0 * TW + tx0, 0);   // spiral cell 0: own pixel
+    for (int d = 1; d <= g.r; d++) {
+        if (__all_sync(0xffffffffu, n >= kmax)) break;
+        const uint32_t fm = (2 * d >= 32) ? 0xffffffffu : ((1u << (2 * d)) - 1u);
+        const int cbase = (2 * d - 1) * (2 * d - 1);
+        // leg 0: x = +d, y = -d+1 .. d
+        uint32_t m = (n < kmax) ? ((occc[tx0 + d] >> (ty0 - d + 1)) & fm) : 0u;
+        while (m) {
+            const int i = __ffs(m) - 1; m &= m - 1;
+            visit((ty0 - d + 1 + i) * TW + tx0 + d, cbase + i);
+            if (n >= kmax) m = 0;
+        }
+        // leg 1: y = +d, x = d-1 .. -d   (descending: reverse the field)
+        m = (n < kmax) ? (__brev((occr[ty0 + d] >> (tx0 - d)) & fm) >> (32 - 2 * d)) : 0u;
+        while (m) {
+            const int i = __ffs(m) - 1; m &= m - 1;
+            visit((ty0 + d) * TW + tx0 + d - 1 - i, cbase + 2 * d + i);
+            if (n >= kmax) m = 0;
+        }
+        // leg 2: x = -d, y = d-1 .. -d
+        m = (n < kmax) ? (__brev((occc[tx0 - d] >> (ty0 - d)) & fm) >> (32 - 2 * d)) : 0u;
+        while (m) {
+            const int i = __ffs(m) - 1; m &= m - 1;
+            visit((ty0 + d - 1 - i) * TW + tx0 - d, cbase + 4 * d + i);
+            if (n >= kmax) m = 0;
+        }
+        // leg 3: y = -d, x = -d+1 .. d
+        m = (n < kmax) ? ((occr[ty0 - d] >> (tx0 - d + 1)) & fm) : 0u;
+        while (m) {
+            const int i = __ffs(m) - 1; m &= m - 1;
+            visit((ty0 - d) * TW + tx0 - d + 1 + i, cbase + 6 * d + i);
+            if (n >= kmax) m = 0;
         }
     }
     n_out = active ? n : 0;
@@ -157,6 +227,8 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     short *s_sp2 = s_sp + g.ncell;                                      // [ncell]  dy*TW + dx
     uint16_t *s_order = (uint16_t *)(s_sp2 + g.ncell);                  // [BL_THREADS]
     uint32_t *s_acc = (uint32_t *)(smem_raw + bl_acc_offset(g));        // [K-1][BL_THREADS]  record << 10 | cell
+    uint32_t *s_occ_r = s_acc + (DAGR_ELL - 1) * BL_THREADS;            // [BL_NB][THmax] row occupancy bitmasks
+    uint32_t *s_occ_c = s_occ_r + BL_NB * THmax;                        // [BL_NB][TWmax] column occupancy bitmasks
     unsigned char *s_colv = (unsigned char *)(s_order + BL_THREADS);    // [TWmax]
     unsigned char *s_rowv = s_colv + TWmax;                             // [THmax]
 
@@ -276,6 +348,23 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         if (!bucketed || !T.unsorted) break;                            // block-uniform
         bucketed = false;                                               // records not time-sorted: redo without buckets
     }
+    // ---- occupancy bitmasks of the bucket ranges (ring walk) ---------------------------------------------
+    const bool use_rings = TW <= 32 && TH <= 32 && g.r <= 15;           // block-uniform
+    if (use_rings) {
+        for (int i = threadIdx.x; i < BL_NB * TH; i += blockDim.x) {
+            const int e = i / TH, ty = i % TH;
+            uint32_t mk = 0;
+            for (int tx = 0; tx < TW; tx++) { const uint32_t rg = s_rng[(ty * TW + tx) * BL_NB + e]; if ((rg >> 8) > (rg & 0xff)) mk |= 1u << tx; }
+            s_occ_r[e * TH + ty] = mk;
+        }
+        for (int i = threadIdx.x; i < BL_NB * TW; i += blockDim.x) {
+            const int e = i / TW, tx = i % TW;
+            uint32_t mk = 0;
+            for (int ty = 0; ty < TH; ty++) { const uint32_t rg = s_rng[(ty * TW + tx) * BL_NB + e]; if ((rg >> 8) > (rg & 0xff)) mk |= 1u << ty; }
+            s_occ_c[e * TW + tx] = mk;
+        }
+        __syncthreads();
+    }
     // ---- thread <-> event assignment in arrival order (time-homogeneous warps) ------------------------
     const int nown = p1 - p0;
     const int own_off = staged ? (p0 - T.run_start[1] + T.run_off[1]) : 0;
@@ -313,24 +402,29 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         if (bucketed) eb = min(max(me.x / dtw - sbase, 0), BL_NB - 1);
         int n;
         const int tidx0 = ty0 * TW + tx0;
-        if (staged) bl_probe<true>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
-        else        bl_probe<false>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
-        // events still unsaturated after BL_R1 cells continue warp-cooperatively (32 cells per step), one at a time
-        if (BL_R1 < g.ncell) {
-            unsigned todo = __ballot_sync(0xffffffffu, active && n < g.K - 1);
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int ep = __shfl_sync(0xffffffffu, p, src);
-                const int2 eme = make_int2(__shfl_sync(0xffffffffu, me.x, src), __shfl_sync(0xffffffffu, me.y, src));
-                const int eeb = __shfl_sync(0xffffffffu, eb, src), etidx = __shfl_sync(0xffffffffu, tidx0, src);
-                const int en = __shfl_sync(0xffffffffu, n, src);
-                const int owner = (int)(threadIdx.x & ~31u) + src;
-                const int nn = staged ? bl_probe_coop<true>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off)
-                                      : bl_probe_coop<false>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off);
-                if ((int)(threadIdx.x & 31) == src) n = nn;
+        if (use_rings) {
+            if (staged) bl_probe_rings<true>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_ti, ti, s_acc, nbr, off, n);
+            else        bl_probe_rings<false>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_ti, ti, s_acc, nbr, off, n);
+        } else {
+            if (staged) bl_probe<true>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+            else        bl_probe<false>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+            // events still unsaturated after BL_R1 cells continue warp-cooperatively (32 cells per step), one at a time
+            if (BL_R1 < g.ncell) {
+                unsigned todo = __ballot_sync(0xffffffffu, active && n < g.K - 1);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int ep = __shfl_sync(0xffffffffu, p, src);
+                    const int2 eme = make_int2(__shfl_sync(0xffffffffu, me.x, src), __shfl_sync(0xffffffffu, me.y, src));
+                    const int eeb = __shfl_sync(0xffffffffu, eb, src), etidx = __shfl_sync(0xffffffffu, tidx0, src);
+                    const int en = __shfl_sync(0xffffffffu, n, src);
+                    const int owner = (int)(threadIdx.x & ~31u) + src;
+                    const int nn = staged ? bl_probe_coop<true>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off)
+                                          : bl_probe_coop<false>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off);
+                    if ((int)(threadIdx.x & 31) == src) n = nn;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
         if (active) nbr[(int64_t)(DAGR_ELL - 1) * N + p] = n;
         // phase B: A_u = sum_e tab[c_e][u] * (polarity_src, x_src/W, y_src/H), converged over the ELL slots;

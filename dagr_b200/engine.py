@@ -145,6 +145,11 @@ class Engine:
         s, b = _fold_bn(cb.norm); _fill(pb.scale, s); _fill(pb.shift, b)
         s, b = _fold_bn(cb.norm_skip); _fill(pb.sscale, s); _fill(pb.sshift, b)
         pb.relu = 1
+        for i in range(3):
+            pb.xs[i] = geom.slots_x[i]
+        for j in range(5):
+            pb.ys[j] = geom.slots_y[j]
+        pb.den_x, pb.den_y = geom.den1_x, geom.den1_y
         pk = dict(l1b=pb, l1a=None, l1img=None)
         if cin0 == 3:
             pa = _lib.L1AParams()

@@ -178,11 +178,19 @@ class Geometry:
         ax = d[:, 0] / (2 * M * W) + 0.5
         ay = d[:, 1] / (2 * M * H) + 0.5
         basis, slot = spline_basis_deg1(torch.stack([ax, ay], dim=1), kernel_size)
-        used = sorted(set(slot[basis != 0].tolist()) | {int(slot[0, 0])})
-        if len(used) > _lib.KU:
-            raise ValueError("more than 9 spline kernel slots reachable at the event level")
-        used = used + [u for u in range(kernel_size ** 2) if u not in used][: _lib.KU - len(used)]
-        self.slots1 = used                                         # slot ids, length 9
+        # reachable spline kernels form a product grid xs x ys (<= 3 x 5): slot id = sx + ks*sy
+        nz = slot[basis != 0]
+        xs = sorted(set((nz % kernel_size).tolist()) | {int(slot[0, 0]) % kernel_size})
+        ys = sorted(set((nz // kernel_size).tolist()) | {int(slot[0, 0]) // kernel_size})
+        if len(xs) > 3 or len(ys) > 5:
+            raise ValueError("more than 3 x 5 spline kernel slots reachable at the event level")
+        xs = xs + [u for u in range(kernel_size) if u not in xs][: 3 - len(xs)]
+        ys = ys + [u for u in range(kernel_size) if u not in ys][: 5 - len(ys)]
+        self.slots_x, self.slots_y = xs, ys
+        used = [xs[i] + kernel_size * ys[j] for j in range(5) for i in range(3)]
+        self.den1_x = float(torch.tensor(2 * M * W, dtype=torch.float32))      # init_lut divisor (spline_conv.py:28-29)
+        self.den1_y = float(torch.tensor(2 * M * H, dtype=torch.float32))
+        self.slots1 = used                                         # slot ids, length 15 = 5 (y) x 3 (x)
         tab = torch.zeros((self.ncell, _lib.TABW), dtype=torch.float32)
         for s in range(4):
             for u, sl in enumerate(used):

@@ -163,6 +163,9 @@ typedef struct {
     float scale[16], shift[16];   /* norm                                            */
     float sscale[16], sshift[16]; /* norm_skip                                       */
     int32_t relu;
+    /* slot u = 3*j + i is spline kernel xs[i] + 5*ys[j]; basis evaluated in-kernel at attr = d/den + 0.5 */
+    int32_t xs[3], ys[5];
+    float den_x, den_y;           /* fl32(2*M*W), fl32(2*M*H)  (spline_conv.py:28-29) */
 } dagr_l1b_params_t;
 
 int dagr_l1_conv_a(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, const float *feat_s,

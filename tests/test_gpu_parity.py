@@ -360,6 +360,38 @@ def test_async_incremental_equals_dense(W, H, B, n, chunks):
     assert_close(dec_live, dense_live, tol=1e-5, what="live window after eviction vs dense")
 
 
+def test_forward_vs_committed_golden_fixture():
+    """the committed oracle fixture (tests/golden/forward_dagr_n_240x180.pt): no oracle code runs here."""
+    from dagr_b200 import export
+    from dagr_b200.data import EventBatch
+    fix = torch.load(ROOT / "tests" / "golden" / "forward_dagr_n_240x180.pt")
+    m = fix["meta"]
+    model, args = make_model(m["size"], m["H"], m["W"], seed=m["model_seed"])
+    model.cuda()
+    data = EventBatch(x=fix["x"], pos=fix["pos"], batch=fix["batch"], width=torch.full((m["B"],), m["W"]),
+                      height=torch.full((m["B"],), m["H"]), time_window=torch.full((m["B"],), 1000000), num_graphs=m["B"])
+    dec, _, _ = _run_graph(model, data, m["B"])
+    eng, L = model.engine, model.engine.last
+    assert torch.equal(eng.export_edges().cpu().int(), fix["edge_index"])
+    N = L["N"]
+    assert_close(export.unsort_rows(eng.xa_rows(), L["ws"]["perm"], N).cpu(), fix["x1a"], what="golden x1a")
+    assert_close(export.unsort_rows(L["x1"], L["ws"]["perm"], N).cpu(), fix["x1"], what="golden x1")
+    for lv in range(4):
+        nodes = export.grid_nodes(L["grids"][lv], L["geom"].levels[lv], L["geom"])
+        amb = fix["level_ambiguous"][lv]
+        same = nodes["pos"].cpu() == fix["level_pos"][lv]
+        assert torch.equal(nodes["batch"].cpu().int(), fix["level_batch"][lv]) and bool(same[~amb].all())
+        if not bool(same.all()):
+            break
+        assert torch.equal(export.grid_edges(L["grids"][lv], L["geom"].levels[lv]).cpu().int(), fix["level_edges"][lv])
+        if lv < 2:
+            assert_close(nodes["x"].cpu(), fix["level_x"][lv], what=f"golden level {lv}")
+    else:
+        assert_close(dec.cpu(), fix["decoded"], what="golden decoded")
+        dets = model(data.clone().cuda())[0]
+        assert [len(d["boxes"]) for d in dets] == fix["n_det"]
+
+
 def test_batch_independence_and_full_size_properties():
     """config-2 shape (640x480, B=8, 300k events/sample): size-independent properties."""
     W, H, B, n = 640, 480, 8, 300000

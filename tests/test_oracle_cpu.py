@@ -263,3 +263,18 @@ def test_oracle_full_forward_runs_and_is_deterministic():
     ref_b = RefModel(model.state_dict(), args, 180, 240, use_lut=False)
     o3 = ref_b.forward(data.x, data.pos, data.batch, 1)
     assert_close(o3["x1"], o1["x1"], tol=1e-3, what="basis vs LUT layer-1")
+
+
+def test_oracle_reproduces_committed_golden_forward():
+    """tests/golden/forward_dagr_n_240x180.pt (made by tests/golden/make_forward_golden.py) is reproduced bit for bit by
+    the oracle on this machine: seeds, weights and the CPU restatement are stable."""
+    from oracle.ref_model import RefModel
+    fix = torch.load(GOLD / "forward_dagr_n_240x180.pt")
+    m = fix["meta"]
+    model, args = make_model(m["size"], m["H"], m["W"], seed=m["model_seed"])
+    cs = float(sum(v.double().abs().sum() for v in model.state_dict().values() if v.dtype.is_floating_point))
+    assert abs(cs - fix["weight_checksum"]) <= 1e-6 * abs(cs)
+    o = RefModel(model.state_dict(), args, m["H"], m["W"]).forward(fix["x"], fix["pos"], fix["batch"], m["B"])
+    assert torch.equal(o["edge_index"].int(), fix["edge_index"])
+    assert torch.allclose(o["decoded"], fix["decoded"], rtol=1e-6, atol=1e-6)
+    assert [len(d["boxes"]) for d in o["detections"]] == fix["n_det"]
