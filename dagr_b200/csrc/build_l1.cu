@@ -386,7 +386,9 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         // arrival ranks are dealt round-robin to the warps: every warp gets the same share of the old
         // (unsaturated, slow) events of the voxel, so no warp is the straggler of the CTA
         const int nw = blockDim.x >> 5;
-        const int rank = (int)(threadIdx.x & 31) * nw + (int)(threadIdx.x >> 5);
+        // ring walk: warps of similar age leave the ring loop together -> contiguous arrival ranks per warp;
+        // cell walk (fallback): ranks dealt round-robin so that no warp is the straggler
+        const int rank = use_rings ? (int)threadIdx.x : (int)(threadIdx.x & 31) * nw + (int)(threadIdx.x >> 5);
         bool active = rank < chunk;
         const int p = p0 + pb0 + (active ? (int)s_order[rank] : 0);
         int x = 0, y = 0;

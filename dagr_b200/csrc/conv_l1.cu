@@ -483,11 +483,12 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     for (int pb0 = p0; pb0 < p1; pb0 += blockDim.x) {
         const int p = pb0 + threadIdx.x;
         const bool inrange = p < p1;
-        const int2 rec = inrange ? ti[p] : make_int2(0, 0);
-        const uint32_t wxy = inrange ? xyb[p] : 0u;
-        if (inrange) { sx += wxy & 0xfff; sy += (wxy >> 12) & 0xfff; st += rec.x; tm = max(tm, rec.x); }
-        const bool active = inrange && rec.y >= min_idx;                 // incremental mode: only new nodes are convolved
-        if (!__syncthreads_or(active)) continue;                         // block-uniform: nothing to do in this chunk
+        // incremental mode: only new nodes are convolved (the arrival index is only looked at then)
+        const bool active = inrange && (min_idx <= 0 || ti[p].y >= min_idx);
+        if (min_idx > 0 && !__syncthreads_or(active)) {                  // block-uniform: nothing new in this chunk
+            if (inrange) { const uint32_t w0 = xyb[p]; const int t0 = ti[p].x; sx += w0 & 0xfff; sy += (w0 >> 12) & 0xfff; st += t0; tm = max(tm, t0); }
+            continue;
+        }
         const int n = active ? nbr[(int64_t)(DAGR_ELL - 1) * N + p] : 0;
         // stage this node's ELL row (independent loads -> one global latency); neighbour positions become staged rows
         if (staged && active) {
@@ -542,10 +543,12 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
                 }
             }
         }
+        if (inrange) { const uint32_t w0 = xyb[p]; const int t0 = ti[p].x; sx += w0 & 0xfff; sy += (w0 >> 12) & 0xfff; st += t0; tm = max(tm, t0); }
         if (!active) continue;
         float o[16];
 #pragma unroll
         for (int c = 0; c < 8; c++) { o[2 * c] = o2[c].x; o[2 * c + 1] = o2[c].y; }
+        const uint32_t wxy = xyb[p];
         const int x = wxy & 0xfff, y = (wxy >> 12) & 0xfff;
         float skv[16];
         if (skip_pre != nullptr) {
