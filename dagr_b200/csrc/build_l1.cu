@@ -487,12 +487,13 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
             o[k] = P.relu ? fmaxf(r, 0.f) : r;
         }
         // xa is stored half-major [2][N][8] so that conv_b can stage one 32-byte channel half per pass
+        const int sw = XA_SWZ(p);
         float4 *dst = reinterpret_cast<float4 *>(xa + (int64_t)p * 8);
-        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        dst[sw] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[sw ^ 1] = make_float4(o[4], o[5], o[6], o[7]);
         dst = reinterpret_cast<float4 *>(xa + (N + (int64_t)p) * 8);
-        dst[0] = make_float4(o[8], o[9], o[10], o[11]);
-        dst[1] = make_float4(o[12], o[13], o[14], o[15]);
+        dst[sw] = make_float4(o[8], o[9], o[10], o[11]);
+        dst[sw ^ 1] = make_float4(o[12], o[13], o[14], o[15]);
     }
     mloc = __reduce_or_sync(0xffffffffu, mloc);
     if ((threadIdx.x & 31) == 0 && mloc) atomicOr(&s_mask, mloc);

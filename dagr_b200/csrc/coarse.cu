@@ -692,29 +692,27 @@ k_postprocess_nms(const float *__restrict__ pred, int A, int nc, float conf_thre
         }
     }
     __syncthreads();
+    __shared__ short s_keep[NMS_MAX];
+    __shared__ int nout;
     if (threadIdx.x == 0) {
         uint32_t dead[NMS_MAX / 32];
         for (int wd = 0; wd < nwords; wd++) dead[wd] = 0;
-        for (int i = 0; i < n; i++) {
-            if ((dead[i >> 5] >> (i & 31)) & 1u) { alive[order[i]] = 0; continue; }
-            for (int wd = i >> 5; wd < nwords; wd++) dead[wd] |= supp[i][wd];
-        }
-    }
-    __syncthreads();
-    // compact survivors in score order; stage through shared (reuse bx rows as 6-float records is too small) ->
-    // serial compaction by one warp keeps it simple (A <= 1024)
-    __shared__ float stage[NMS_MAX][6];
-    __shared__ int nout;
-    if (threadIdx.x == 0) {
         int m = 0;
         for (int i = 0; i < n; i++) {
-            const int a = order[i];
-            if (alive[a]) { for (int k = 0; k < 6; k++) stage[m][k] = D[a * 6 + k]; m++; }
+            if ((dead[i >> 5] >> (i & 31)) & 1u) continue;
+            s_keep[m++] = order[i];
+            for (int wd = i >> 5; wd < nwords; wd++) dead[wd] |= supp[i][wd];
         }
         nout = m;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < A * 6; i += blockDim.x) D[i] = (i / 6 < nout) ? stage[i / 6][i % 6] : 0.f;
+    // compact survivors in score order: gather into registers first (the raw records live in D itself)
+    float vals[(NMS_MAX * 6 + 255) / 256];
+    int cnt = 0;
+    for (int i = threadIdx.x; i < A * 6; i += blockDim.x, cnt++) vals[cnt] = (i / 6 < nout) ? D[s_keep[i / 6] * 6 + i % 6] : 0.f;
+    __syncthreads();
+    cnt = 0;
+    for (int i = threadIdx.x; i < A * 6; i += blockDim.x, cnt++) D[i] = vals[cnt];
     if (threadIdx.x == 0) ndet[b] = nout;
 }
 

@@ -26,6 +26,11 @@ void dagr_set_error(const char *fmt, ...);
 
 static inline int dagr_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// xa rows are stored half-major [2][N][8]; inside each 32-byte half-row the two 16-byte chunks are swapped when bit 2 of
+// the row index is set.  A staged copy of the rows (TMA keeps them contiguous) then spreads a warp's random row gathers
+// over all eight 16-byte bank groups instead of four (LDS.128 conflict degree ~3.4 -> ~2.3).
+#define XA_SWZ(p) ((int)(((p) >> 2) & 1))
+
 // order-preserving float <-> uint32 encoding (0 is below every encoded value -> "empty")
 __device__ __forceinline__ uint32_t enc_ordered(float f)
 {

@@ -119,12 +119,13 @@ k_l1_conv_a(const dagr_geom_t g, int64_t N, const uint32_t *__restrict__ xyb, co
         o[k] = P.relu ? fmaxf(r, 0.f) : r;
     }
     // xa is stored half-major: [2][N][8] (channels 0-7, then 8-15), see conv_b v2
+    const int sw = XA_SWZ(p);
     float4 *dst = reinterpret_cast<float4 *>(xa + p * 8);
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    dst[sw] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[sw ^ 1] = make_float4(o[4], o[5], o[6], o[7]);
     dst = reinterpret_cast<float4 *>(xa + (N + p) * 8);
-    dst[0] = make_float4(o[8], o[9], o[10], o[11]);
-    dst[1] = make_float4(o[12], o[13], o[14], o[15]);
+    dst[sw] = make_float4(o[8], o[9], o[10], o[11]);
+    dst[sw ^ 1] = make_float4(o[12], o[13], o[14], o[15]);
 }
 
 extern "C" int dagr_l1_conv_a(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, const float *feat_s,
@@ -172,7 +173,7 @@ k_l1_conv_b(const dagr_geom_t g, int64_t N, const uint32_t *__restrict__ xyb, co
             {
                 // self loop (spiral cell 0) and root weight: own row
                 const float4 *src = reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + p) * 8);
-                const float4 t0 = src[0], t1 = src[1];
+                const float4 t0 = src[XA_SWZ(p)], t1 = src[XA_SWZ(p) ^ 1];
                 const float2 v[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
                 float t[DAGR_KU];
                 load_tab(s.tab, t);
@@ -203,7 +204,7 @@ k_l1_conv_b(const dagr_geom_t g, int64_t N, const uint32_t *__restrict__ xyb, co
                 const int j = nbr[(int64_t)q * N + p];
                 const int c = off[(int64_t)q * N + p];
                 const float4 *src = reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + j) * 8);
-                const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                const float4 t0 = __ldg(src + XA_SWZ(j)), t1 = __ldg(src + (XA_SWZ(j) ^ 1));
                 const float2 e[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
                 float t[DAGR_KU];
                 load_tab(s.tab + c * DAGR_TABW, t);
@@ -364,17 +365,17 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, int half, int 
         for (int k = 0; k < 4; k++) A[u][k] = make_float2(0.f, 0.f);
     const float *tabg = s_tab + (size_t)grp * ncell * 8;
     for (int q = -1; q < n; q++) {                                       // q = -1: self loop (spiral cell 0)
-        int row, c;
-        if (q < 0) { row = STAGED ? own_row : p; c = 0; }
+        int row, c, sw;
+        if (q < 0) { row = STAGED ? own_row : p; c = 0; sw = XA_SWZ(p); }
         else if (STAGED) {
             const uint32_t ell = s_ell[q * CB2_THREADS + threadIdx.x];
-            row = (int)(ell >> 12); c = (int)(ell & 0xfff);
+            row = (int)(ell >> 12); c = (int)(ell & 0x7ff); sw = (int)((ell >> 11) & 1u);
         } else {
-            row = nbr[(int64_t)q * N + p]; c = off[(int64_t)q * N + p];
+            row = nbr[(int64_t)q * N + p]; c = off[(int64_t)q * N + p]; sw = XA_SWZ(row);
         }
         const float4 *src = STAGED ? reinterpret_cast<const float4 *>(s_rows + (int64_t)row * 8)
                                    : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + row) * 8);
-        const float4 t0 = src[0], t1 = src[1];
+        const float4 t0 = src[sw], t1 = src[sw ^ 1];
         const float2 e[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
         const float4 w0 = *reinterpret_cast<const float4 *>(tabg + c * 8);
         const float w4 = tabg[c * 8 + 4];
@@ -502,7 +503,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             for (int q = 0; q < DAGR_ELL - 1; q++) {
                 const int j = jj[q];
                 const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
-                s_ell[q * CB2_THREADS + threadIdx.x] = ((uint32_t)row << 12) | (uint32_t)cc[q];
+                s_ell[q * CB2_THREADS + threadIdx.x] = ((uint32_t)row << 12) | ((uint32_t)XA_SWZ(j) << 11) | (uint32_t)cc[q];
             }
         }
         float2 o2[8];
@@ -528,7 +529,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
                 {
                     const float4 *src = staged ? reinterpret_cast<const float4 *>(s_rows + (int64_t)(p + d1) * 8)
                                                : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + p) * 8);
-                    const float4 t0 = src[0], t1 = src[1];
+                    const float4 t0 = src[XA_SWZ(p)], t1 = src[XA_SWZ(p) ^ 1];
                     const float v[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
                     for (int k = 0; k < 8; k++)
@@ -629,7 +630,7 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
 {
     DAGR_CHECK_ARG(g && p_host, "null argument");
     const int cells = g->B * g->ny1 * g->nx1;
-    DAGR_CHECK_ARG(g->ncell <= 4096, "spiral cell index must fit 12 bits");
+    DAGR_CHECK_ARG(g->ncell <= 2048, "spiral cell index must fit 11 bits");
     const size_t smem = (size_t)CB2_CAP * 32 + (size_t)CB2_NG * g->ncell * 8 * 4 + (size_t)(DAGR_ELL - 1) * CB2_THREADS * 4;
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -653,7 +654,7 @@ __global__ void k_xa_permute(int64_t N, const int32_t *__restrict__ perm, int n_
     const int q = (int)(t & 3);
     if (p >= N) return;
     const int i = perm[p];
-    float4 *srt = reinterpret_cast<float4 *>(xa_sorted + ((int64_t)(q >> 1) * N + p) * 8) + (q & 1);
+    float4 *srt = reinterpret_cast<float4 *>(xa_sorted + ((int64_t)(q >> 1) * N + p) * 8) + ((q & 1) ^ XA_SWZ(p));
     float4 *arr = reinterpret_cast<float4 *>(xa_arrival + (int64_t)i * 16) + q;
     if (scatter) { if (i >= n_old) *arr = *srt; }
     else         { if (i < n_old) *srt = *arr; }

@@ -162,12 +162,13 @@ k_l1_conv_a_image(const dagr_geom_t g, int64_t N, const float *__restrict__ x0, 
         o[c] = P->relu ? fmaxf(r, 0.f) : r;
         sk[c] = fmaf(sk[c], P->sscale[c], P->sshift[c]);
     }
+    const int sw = XA_SWZ(p);
     float4 *dst = reinterpret_cast<float4 *>(xa + p * 8);
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    dst[sw] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[sw ^ 1] = make_float4(o[4], o[5], o[6], o[7]);
     dst = reinterpret_cast<float4 *>(xa + (N + p) * 8);
-    dst[0] = make_float4(o[8], o[9], o[10], o[11]);
-    dst[1] = make_float4(o[12], o[13], o[14], o[15]);
+    dst[sw] = make_float4(o[8], o[9], o[10], o[11]);
+    dst[sw ^ 1] = make_float4(o[12], o[13], o[14], o[15]);
     float4 *sd = reinterpret_cast<float4 *>(skipv + p * 16);
     sd[0] = make_float4(sk[0], sk[1], sk[2], sk[3]);
     sd[1] = make_float4(sk[4], sk[5], sk[6], sk[7]);

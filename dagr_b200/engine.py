@@ -477,7 +477,11 @@ class Engine:
         (the kernels keep them half-major, [2][N][8])."""
         L = self.last
         N, xa = L["N"], L["ws"]["xa"]
-        return torch.cat([xa[:N * 8].view(N, 8), xa[N * 8:2 * N * 8].view(N, 8)], dim=1)
+        rows = torch.cat([xa[:N * 8].view(N, 8), xa[N * 8:2 * N * 8].view(N, 8)], dim=1).clone()
+        sw = ((torch.arange(N, device=rows.device) >> 2) & 1).bool()       # XA_SWZ: 16-byte chunks swapped on these rows
+        r = rows[sw].view(-1, 2, 2, 4)
+        rows[sw] = r.flip(2).reshape(-1, 16)
+        return rows
 
     @torch.no_grad()
     def postprocess(self, decoded: torch.Tensor, conf_thre, nms_thre, width, height, filtering=True):
