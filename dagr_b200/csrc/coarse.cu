@@ -460,7 +460,10 @@ __global__ void k_grid_pool(const dagr_grid_t ch, const dagr_grid_t pa, const in
         atomicAdd(possum + 3 * (int64_t)P + 0, (double)ch.posxr[px]);
         atomicAdd(possum + 3 * (int64_t)P + 1, (double)ch.posyr[py]);
         atomicAdd(possum + 3 * (int64_t)P + 2, (double)tmean[cell]);
-        atomicMax(ptmax + P, enc_ordered(tmax[cell]));
+        // t_max of the parent = max over its children of THEIR position t, i.e. the child's mean t (pooling.py:70 reads
+        // data.pos[:, -1], which after the previous pooling is pool_pos' mean) -- not the max of the children's t_max
+        atomicMax(ptmax + P, enc_ordered(tmean[cell]));
+        (void)tmax;
         const uint32_t m = mask[cell];
         uint32_t bits = 0;
         for (int bit = 0; bit < 9; bit++) {

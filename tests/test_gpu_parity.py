@@ -209,6 +209,8 @@ FWD_CASES = [
     (240, 180, 1, 6000, "uniform", "n", "ncaltech101"),
     (320, 215, 2, 12000, "clustered", "s", "dsec"),
     (640, 480, 2, 25000, "uniform", "s", "dsec"),
+    (320, 215, 1, 8000, "clustered", "l", "dsec"),            # widest variant: C = 128 (Cin 130 at the coarse levels)
+    (240, 180, 2, 5000, "uniform", "m", "dsec"),
 ]
 
 
@@ -390,6 +392,45 @@ def test_forward_vs_committed_golden_fixture():
         assert_close(dec.cpu(), fix["decoded"], what="golden decoded")
         dets = model(data.clone().cuda())[0]
         assert [len(d["boxes"]) for d in dets] == fix["n_det"]
+
+
+def test_keep_temporal_ordering_filters_coarse_edges_like_the_reference():
+    """--keep_temporal_ordering (pooling.py:69-72): coarse edges survive only if t_max[dst] > t_max[src]."""
+    from dagr_b200 import export
+    from oracle.ref_model import RefModel
+    W, H, B = 240, 180, 2
+    model, args = make_model("n", H, W, keep_temporal_ordering=True)
+    model.cuda()
+    raw, data = make_inputs(B, 4000, W, H, seed=17, kind="clustered")
+    dec, _, _ = _run_graph(model, data, B)
+    L = model.engine.last
+    o = RefModel({k: v.cpu() for k, v in model.state_dict().items()}, args, H, W).forward(data.x, data.pos, data.batch, B)
+    for lv in range(4):
+        pl = o["levels"][lv]
+        nodes = export.grid_nodes(L["grids"][lv], L["geom"].levels[lv], L["geom"])
+        if not bool((nodes["pos"].cpu() == pl["pos"][:, :2]).all()):
+            pytest.skip("ambiguous pooled position")
+        assert torch.equal(export.grid_edges(L["grids"][lv], L["geom"].levels[lv]).cpu(), pl["edge_index"]), f"level {lv}"
+    assert_close(dec.cpu(), o["decoded"], what="decoded (keep_temporal_ordering)")
+
+
+def test_interframe_growing_windows_like_run_test_interframe():
+    """scripts/run_test_interframe.py:83-86: synchronous forward on windows num_us = linspace(0, 50000, steps), first one empty."""
+    from dagr_b200.data import EventBatch
+    W, H, B = 320, 215, 2
+    model, args = make_model("s", H, W)
+    model.cuda()
+    raw, data = make_inputs(B, 20000, W, H, seed=23, kind="uniform")
+    t_us = (data.pos[:, 2].double() * 1e6).round()
+    counts = []
+    for n_us in np.linspace(0, 50000, 5):
+        m = t_us < (950000 + n_us)
+        d = EventBatch(x=data.x[m], pos=data.pos[m], batch=data.batch[m], width=data.width, height=data.height,
+                       time_window=data.time_window, num_graphs=B)
+        dets = model(d.cuda())[0]
+        assert len(dets) == B and all(torch.isfinite(x["boxes"]).all() for x in dets)
+        counts.append(int(m.sum()))
+    assert counts[0] == 0 and counts[-1] == len(t_us)
 
 
 def test_batch_independence_and_full_size_properties():
