@@ -11,7 +11,7 @@
 // Voxels whose neighbourhood does not fit the staging buffer fall back to probing global memory.
 #include "common.cuh"
 
-#define BL_THREADS 192           // >= events of a voxel at the nominal density (Poisson mean 134): one pass
+#define BL_THREADS 160           // >= events of a voxel at the nominal density (Poisson mean 134): one pass
 #define BL_CAP 2048              // staged neighbourhood records per CTA (uniform 300k events/sample: ~1200)
 #define BL_NB 8                  // time buckets of width delta_t kept per tile pixel
 
@@ -228,7 +228,6 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     uint16_t *s_order = (uint16_t *)(s_sp2 + g.ncell);                  // [BL_THREADS]
     uint32_t *s_acc = (uint32_t *)(smem_raw + bl_acc_offset(g));        // [K-1][BL_THREADS]  record << 10 | cell
     uint32_t *s_occ_r = s_acc + (DAGR_ELL - 1) * BL_THREADS;            // [BL_NB][THmax] row occupancy bitmasks
-    uint32_t *s_occ_c = s_occ_r + BL_NB * THmax;                        // [BL_NB][TWmax] column occupancy bitmasks
     unsigned char *s_colv = (unsigned char *)(s_order + BL_THREADS);    // [TWmax]
     unsigned char *s_rowv = s_colv + TWmax;                             // [THmax]
 
@@ -251,6 +250,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     }
     __syncthreads();
     const int TW = T.TW, TH = T.TH, TP = TW * TH;
+    uint32_t *s_occ_c = s_occ_r + BL_NB * TH;                           // [BL_NB][TW] column occupancy bitmasks
     const int total = T.run_off[2] + T.run_len[2];
     const bool staged = total <= BL_CAP;                                // block-uniform
     const int bbase = b * per * g.CP;
@@ -317,7 +317,12 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     // bucket(t) = clamp(t/delta_t - (smin-1), 0, NB-1); an event in bucket e needs records of buckets {e-1, e}.
     const int sbase = T.smin - 1;
     bool bucketed = staged && (T.smax - sbase) < BL_NB && (flags == nullptr || flags[0] == 0);   // block-uniform
+    const bool use_rings = TW <= 32 && TH <= 32 && g.r <= 15;           // block-uniform
     for (int pass = 0; pass < 2; pass++) {
+        if (use_rings) {
+            for (int i = threadIdx.x; i < BL_NB * (TH + TW); i += blockDim.x) s_occ_r[i] = 0u;   // s_occ_c follows s_occ_r
+            __syncthreads();
+        }
         for (int i = threadIdx.x; i < TP; i += blockDim.x) {
             const uint32_t pb = s_pbin[i];
             const int vis = pb & 0xff, base = pb >> 8;
@@ -338,32 +343,20 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
 #pragma unroll
                 for (int q = 1; q <= BL_NB; q++) cum[q] = (unsigned char)vis;
             }
+            const int oty = i / TW, otx = i % TW;
 #pragma unroll
             for (int e = 0; e < BL_NB; e++) {
                 const int lo = cum[e > 0 ? e - 1 : 0], hi = cum[e + 1];
                 s_rng[i * BL_NB + e] = (uint16_t)(lo | (hi << 8));
+                if (use_rings && hi > lo) {                              // occupancy bitmasks for the ring walk
+                    atomicOr(&s_occ_r[e * TH + oty], 1u << otx);
+                    atomicOr(&s_occ_c[e * TW + otx], 1u << oty);
+                }
             }
         }
         __syncthreads();
         if (!bucketed || !T.unsorted) break;                            // block-uniform
         bucketed = false;                                               // records not time-sorted: redo without buckets
-    }
-    // ---- occupancy bitmasks of the bucket ranges (ring walk) ---------------------------------------------
-    const bool use_rings = TW <= 32 && TH <= 32 && g.r <= 15;           // block-uniform
-    if (use_rings) {
-        for (int i = threadIdx.x; i < BL_NB * TH; i += blockDim.x) {
-            const int e = i / TH, ty = i % TH;
-            uint32_t mk = 0;
-            for (int tx = 0; tx < TW; tx++) { const uint32_t rg = s_rng[(ty * TW + tx) * BL_NB + e]; if ((rg >> 8) > (rg & 0xff)) mk |= 1u << tx; }
-            s_occ_r[e * TH + ty] = mk;
-        }
-        for (int i = threadIdx.x; i < BL_NB * TW; i += blockDim.x) {
-            const int e = i / TW, tx = i % TW;
-            uint32_t mk = 0;
-            for (int ty = 0; ty < TH; ty++) { const uint32_t rg = s_rng[(ty * TW + tx) * BL_NB + e]; if ((rg >> 8) > (rg & 0xff)) mk |= 1u << ty; }
-            s_occ_c[e * TW + tx] = mk;
-        }
-        __syncthreads();
     }
     // ---- thread <-> event assignment in arrival order (time-homogeneous warps) ------------------------
     const int nown = p1 - p0;
@@ -372,8 +365,8 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     for (int pb0 = 0; pb0 < nown; pb0 += blockDim.x) {
         const int chunk = min((int)blockDim.x, nown - pb0);
         __syncthreads();
-        // rank of each event of the chunk by arrival index
-        if ((int)threadIdx.x < chunk) {
+        // rank of each event of the chunk by arrival index (cell walk only: the ring walk does not need age-sorted warps)
+        if (!use_rings && (int)threadIdx.x < chunk) {
             const int myidx = staged ? s_ti[own_off + pb0 + threadIdx.x].y : ti[p0 + pb0 + threadIdx.x].y;
             int rank = 0;
             for (int k = 0; k < chunk; k++) {
@@ -390,7 +383,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         // cell walk (fallback): ranks dealt round-robin so that no warp is the straggler
         const int rank = use_rings ? (int)threadIdx.x : (int)(threadIdx.x & 31) * nw + (int)(threadIdx.x >> 5);
         bool active = rank < chunk;
-        const int p = p0 + pb0 + (active ? (int)s_order[rank] : 0);
+        const int p = p0 + pb0 + (active ? (use_rings ? rank : (int)s_order[rank]) : 0);
         int x = 0, y = 0;
         int2 me = make_int2(0, 0);
         if (active) {
