@@ -42,6 +42,8 @@ def parse():
     p.add_argument("--kind", default="uniform", choices=["uniform", "clustered"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work for the baseline sample")
+    p.add_argument("--extras", action="store_true", help="also measure config 3 (image fusion, inter-frame steps) and "
+                   "config 5 (streaming, 1 ms chunks) and attach them as `extras` (not part of the headline)")
     return p.parse_args()
 
 
@@ -145,6 +147,76 @@ def cpu_calibrate(model_sd, margs, raw):
 
 def margs_size(a):
     return {0.25: "n", 0.5: "s", 0.75: "m", 1.0: "l"}.get(float(a.net_stem_width), "?")
+
+
+def measure_extras(a, margs, dev):
+    """config 3: dagr-s + ResNet-50 image fusion, run_test_interframe-style windows (num_us = linspace(0, 50 ms, 10));
+    config 5 shape: one stream, 1 ms chunks appended to a 50 ms history through the incremental engine."""
+    import numpy as np
+    from dagr_b200.asynchronous import AsyncDAGR
+    from dagr_b200.data import EventBatch, format_data, synth_batch
+    from dagr_b200.model.dagr import DAGR
+    from dagr_b200.utils.args import default_args
+    from tests.helpers import randomize_bn
+    out = {}
+    # ---- config 3 ---------------------------------------------------------------------------------
+    torch.manual_seed(0)
+    iargs = default_args(a.size, batch_size=a.batch, use_image=True, img_net="resnet50")
+    m3 = randomize_bn(DAGR(iargs, height=H, width=W).eval()).to(dev)
+    raw = synth_batch(a.batch, a.events, W, H, seed=4242, kind=a.kind, with_image=True)
+    d = format_data(raw.clone().to(dev))
+    t_us = (d.pos[:, 2].double() * T).round()
+    lat = []
+    for n_us in np.linspace(0, 50000, 10):
+        msk = t_us < (T - 50000 + n_us)
+        sub = EventBatch(x=d.x[msk], pos=d.pos[msk], batch=d.batch[msk], width=d.width, height=d.height, time_window=d.time_window,
+                         image=d.image, num_graphs=a.batch)
+        for _ in range(2):
+            m3(sub.clone())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            m3(sub.clone())
+        e1.record(); torch.cuda.synchronize()
+        lat.append(dict(num_us=int(n_us), events=int(msk.sum()), ms=e0.elapsed_time(e1) / 3))
+    out["config3_interframe"] = dict(model=f"dagr-{a.size} + resnet50 image fusion", batch=a.batch, steps=lat,
+                                     note="full synchronous forward per step incl. cuDNN trunk (fp32/TF32) and NMS")
+    # ---- config 5 shape ------------------------------------------------------------------------------
+    torch.manual_seed(0)
+    m5 = randomize_bn(DAGR(default_args("l", batch_size=1), height=H, width=W).eval()).to(dev)
+    rate = 1_000_000                                            # events / s
+    raw = synth_batch(1, int(rate * 0.1), W, H, seed=99, kind=a.kind, window_us=100_000)
+    d = format_data(raw.clone().to(dev))
+    t_us = (d.pos[:, 2].double() * T).round()
+    t0 = float(t_us.min())
+    def ev(c):
+        return EventBatch(x=d.x[c], pos=d.pos[c], batch=d.batch[c], width=d.width, height=d.height, time_window=d.time_window, num_graphs=1)
+
+    runs = []
+    for chunk_us in (1000, 2000, 5000):
+        eng = AsyncDAGR(m5)
+        eng.step_decoded(ev(t_us < t0 + 50_000), batch_size=1)                       # 50 ms of history
+        chunk_ms = []
+        nch = min(40, 45_000 // chunk_us)
+        for k in range(nch):
+            c = (t_us >= t0 + 50_000 + chunk_us * k) & (t_us < t0 + 50_000 + chunk_us * (k + 1))
+            ch = ev(c)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); eng.step(ch); e1.record(); torch.cuda.synchronize()
+            chunk_ms.append((int(c.sum()), e0.elapsed_time(e1)))
+        skip = min(5, nch // 3)
+        ms = sorted(x[1] for x in chunk_ms[skip:])
+        nev = sum(x[0] for x in chunk_ms[skip:])
+        runs.append(dict(chunk_us=chunk_us, events_per_chunk=nev / len(ms), p50_ms=ms[len(ms) // 2], p99_ms=ms[-1],
+                         sustained_mev_s=nev / (sum(ms) * 1e-3) / 1e6, realtime=bool(ms[len(ms) // 2] * 1e3 <= chunk_us)))
+    out["config5_streaming"] = dict(model="dagr-l", stream_rate_mev_s=rate / 1e6, history_us=50000, runs=runs,
+                                    note="append-only incremental update (dagr_b200.asynchronous), detections after every chunk, "
+                                         "one stream on one GPU; the window grows to <= 95 ms during the measurement (eviction is a "
+                                         "rebuild, see DESIGN.md); a step is host-launch bound (~1.4 ms), so chunks >= 2 ms keep up "
+                                         "with a 1 Mevents/s stream")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -302,6 +374,9 @@ def main():
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
                 e2e=e2e, gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline,
                 interframe_latency_ms=ms)
+
+    if a.extras and world == 1:
+        line["extras"] = measure_extras(a, margs, dev)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

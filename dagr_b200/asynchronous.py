@@ -65,11 +65,15 @@ class AsyncDAGR:
         self.model = model
         self.state = StreamState()
         self._batch = self._pos = self._feat = None
+        self._hb = self._hp = self._hf = None
+        self._n = 0
         self.B = self.W = self.H = None
 
     def reset(self):
         self.state.reset()
         self._batch = self._pos = self._feat = None
+        self._hb = self._hp = self._hf = None
+        self._n = 0
 
     @property
     def num_events(self):
@@ -82,17 +86,26 @@ class AsyncDAGR:
         m = self.model
         batch_i, pos_i, feat, W, H = m._prepare_events(chunk)
         B = int(batch_size or getattr(chunk, "num_graphs", 1) or 1)
-        if self._batch is None:
+        k = int(batch_i.shape[0])
+        if self._hb is None:
             self.B, self.W, self.H = B, W, H
-            self._batch, self._pos, self._feat = batch_i, pos_i, feat
+            self._n = 0
         else:
             assert (B, W, H) == (self.B, self.W, self.H), "stream geometry changed; call reset()"
-            self._batch = torch.cat([self._batch, batch_i])
-            self._pos = torch.cat([self._pos, pos_i])
-            self._feat = torch.cat([self._feat, feat])
+        if self._hb is None or self._n + k > self._hb.shape[0]:          # history buffers grow geometrically
+            cap = max(2 * (self._n + k), 65536)
+            dev = batch_i.device
+            hb, hp, hf = (torch.empty(cap, dtype=torch.int32, device=dev), torch.empty((cap, 3), dtype=torch.int32, device=dev),
+                          torch.empty(cap, dtype=torch.float32, device=dev))
+            if self._hb is not None and self._n:
+                hb[: self._n] = self._hb[: self._n]; hp[: self._n] = self._hp[: self._n]; hf[: self._n] = self._hf[: self._n]
+            self._hb, self._hp, self._hf = hb, hp, hf
+        n0 = self._n
+        self._hb[n0:n0 + k] = batch_i; self._hp[n0:n0 + k] = pos_i; self._hf[n0:n0 + k] = feat
+        self._n = n0 + k
+        self._batch, self._pos, self._feat = self._hb[: self._n], self._hp[: self._n], self._hf[: self._n]
         n_old = self.state.n
-        dec = m.engine.forward_events(self._batch.contiguous(), self._pos.contiguous(), self._feat.contiguous(), self.B, self.W,
-                                      self.H, stream_state=self.state, n_old=n_old)
+        dec = m.engine.forward_events(self._batch, self._pos, self._feat, self.B, self.W, self.H, stream_state=self.state, n_old=n_old)
         self.state.n = self.num_events
         return dec
 
@@ -114,6 +127,7 @@ class AsyncDAGR:
             return
         keep = self._pos[:, 2] >= int(t_us)
         self._batch, self._pos, self._feat = self._batch[keep].contiguous(), self._pos[keep].contiguous(), self._feat[keep].contiguous()
+        self._hb, self._hp, self._hf, self._n = self._batch, self._pos, self._feat, int(self._batch.shape[0])
         self.state.reset()
         dec = self.model.engine.forward_events(self._batch, self._pos, self._feat, self.B, self.W, self.H, stream_state=self.state,
                                                n_old=0)

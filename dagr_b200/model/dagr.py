@@ -117,6 +117,19 @@ class DAGR(YOLOX):
         d["_async"] = None
         return d
 
+    # packed weights follow the module's tensors: repack after anything that can replace or rewrite them
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        if getattr(self, "_engine", None) is not None:
+            self._engine.invalidate()
+        return out
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        if getattr(self, "_engine", None) is not None:
+            self._engine.invalidate()
+        return out
+
     @property
     def engine(self):
         if self._engine is None:
@@ -127,6 +140,8 @@ class DAGR(YOLOX):
     def cache_luts(self, width, height, radius):
         """dagr.py:37-72 (records LUT parameters; see MySplineConv.init_lut)."""
         bb, hd = self.backbone, self.head
+        if self._engine is not None:
+            self._engine.invalidate()
         M = 2 * float(int(radius * width + 2) / width)
         r = int(radius * width + 1)
         bb.conv_block1.conv_block1.conv.init_lut(height=height, width=width, Mx=M, rx=r)
