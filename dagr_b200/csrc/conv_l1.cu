@@ -352,8 +352,8 @@ struct CB2Tile {
 // run-time offset: one copy of the unrolled FFMA block serves all six passes (instruction-cache friendly),
 // and only 40 accumulators are live (no spills, higher occupancy).
 // s_ell[q][tid] = (row << 12) | spiral cell;  s_tab[g][cell][8] holds the 5 slot weights of group g.
-template <bool STAGED>
-__device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, int half, int grp, const float *__restrict__ xa, const float *s_rows,
+template <bool STAGED, int half, int grp>
+__device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *__restrict__ xa, const float *s_rows,
                                          const float *s_tab, const uint32_t *s_ell, const int32_t *__restrict__ nbr,
                                          const uint16_t *__restrict__ off, const dagr_l1b_params_t &P, int own_row, int ncell,
                                          float2 o2[8])
@@ -364,6 +364,7 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, int half, int 
 #pragma unroll
         for (int k = 0; k < 4; k++) A[u][k] = make_float2(0.f, 0.f);
     const float *tabg = s_tab + (size_t)grp * ncell * 8;
+#pragma unroll 2
     for (int q = -1; q < n; q++) {                                       // q = -1: self loop (spiral cell 0)
         int row, c, sw;
         if (q < 0) { row = STAGED ? own_row : p; c = 0; sw = XA_SWZ(p); }
@@ -377,8 +378,9 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, int half, int 
                                    : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + row) * 8);
         const float4 t0 = src[sw], t1 = src[sw ^ 1];
         const float2 e[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
-        const float4 w0 = *reinterpret_cast<const float4 *>(tabg + c * 8);
-        const float w4 = tabg[c * 8 + 4];
+        const int ts = 4 * XA_SWZ(c);
+        const float4 w0 = *reinterpret_cast<const float4 *>(tabg + c * 8 + ts);
+        const float w4 = tabg[c * 8 + (ts ^ 4)];
         const float t[CB2_G] = {w0.x, w0.y, w0.z, w0.w, w4};
 #pragma unroll
         for (int u = 0; u < CB2_G; u++) {
@@ -387,16 +389,21 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, int half, int 
             for (int k = 0; k < 4; k++) A[u][k] = ffma2(tt, e[k], A[u][k]);
         }
     }
+    // phase 2.  The weights sit in the constant bank at a run-time (warp-uniform) offset, i.e. every fetch is an LDC
+    // through the address-divergence unit (~1 per 8 cycles per SM): fetch 128 bits at a time and feed two FFMA2 from it.
     const float (*W)[16][16] = &P.w[grp * CB2_G];
 #pragma unroll
     for (int u = 0; u < CB2_G; u++)
 #pragma unroll
         for (int k = 0; k < 4; k++)
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                // packed fp32x2 FMA: two output channels per instruction, scalar A broadcast
-                o2[c] = ffma2(make_float2(A[u][k].x, A[u][k].x), make_float2(W[u][8 * half + 2 * k][2 * c], W[u][8 * half + 2 * k][2 * c + 1]), o2[c]);
-                o2[c] = ffma2(make_float2(A[u][k].y, A[u][k].y), make_float2(W[u][8 * half + 2 * k + 1][2 * c], W[u][8 * half + 2 * k + 1][2 * c + 1]), o2[c]);
+            for (int c4 = 0; c4 < 4; c4++) {
+                const float4 wa = *reinterpret_cast<const float4 *>(&W[u][8 * half + 2 * k][4 * c4]);
+                const float4 wb = *reinterpret_cast<const float4 *>(&W[u][8 * half + 2 * k + 1][4 * c4]);
+                o2[2 * c4] = ffma2(make_float2(A[u][k].x, A[u][k].x), make_float2(wa.x, wa.y), o2[2 * c4]);
+                o2[2 * c4 + 1] = ffma2(make_float2(A[u][k].x, A[u][k].x), make_float2(wa.z, wa.w), o2[2 * c4 + 1]);
+                o2[2 * c4] = ffma2(make_float2(A[u][k].y, A[u][k].y), make_float2(wb.x, wb.y), o2[2 * c4]);
+                o2[2 * c4 + 1] = ffma2(make_float2(A[u][k].y, A[u][k].y), make_float2(wb.z, wb.w), o2[2 * c4 + 1]);
             }
 }
 
@@ -465,7 +472,8 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int u = v * 4 + k;
-            if (u < DAGR_KU) s_tab[((size_t)(u / CB2_G) * g.ncell + c) * 8 + (u % CB2_G)] = tv[k];
+            // same 16-byte chunk swizzle as the xa rows (XA_SWZ) so that random table rows spread over all bank groups
+            if (u < DAGR_KU) s_tab[((size_t)(u / CB2_G) * g.ncell + c) * 8 + (((u % CB2_G) + 4 * XA_SWZ(c)) & 7)] = tv[k];
         }
     }
     __syncthreads();
@@ -534,14 +542,20 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
 #pragma unroll
                     for (int k = 0; k < 8; k++)
 #pragma unroll
-                        for (int c = 0; c < 8; c++)
-                            o2[c] = ffma2(make_float2(v[k], v[k]), make_float2(P.root[8 * half + k][2 * c], P.root[8 * half + k][2 * c + 1]), o2[c]);
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            const float4 w4 = *reinterpret_cast<const float4 *>(&P.root[8 * half + k][4 * c4]);
+                            o2[2 * c4] = ffma2(make_float2(v[k], v[k]), make_float2(w4.x, w4.y), o2[2 * c4]);
+                            o2[2 * c4 + 1] = ffma2(make_float2(v[k], v[k]), make_float2(w4.z, w4.w), o2[2 * c4 + 1]);
+                        }
                 }
-#pragma unroll 1
-                for (int grp = 0; grp < CB2_NG; grp++) {
-                    if (staged) cb2_pass<true>(N, p, n, half, grp, xa, s_rows, s_tab, s_ell, nbr, off, P, p + d1, g.ncell, o2);
-                    else        cb2_pass<false>(N, p, n, half, grp, xa, s_rows, s_tab, s_ell, nbr, off, P, 0, g.ncell, o2);
-                }
+#define CB2_PASS(H, G)                                                                                               \
+    do {                                                                                                            \
+        if (staged) cb2_pass<true, H, G>(N, p, n, xa, s_rows, s_tab, s_ell, nbr, off, P, p + d1, g.ncell, o2);      \
+        else        cb2_pass<false, H, G>(N, p, n, xa, s_rows, s_tab, s_ell, nbr, off, P, 0, g.ncell, o2);          \
+    } while (0)
+                if (half == 0) { CB2_PASS(0, 0); CB2_PASS(0, 1); CB2_PASS(0, 2); }
+                else           { CB2_PASS(1, 0); CB2_PASS(1, 1); CB2_PASS(1, 2); }
+#undef CB2_PASS
             }
         }
         if (inrange) { const uint32_t w0 = xyb[p]; const int t0 = ti[p].x; sx += w0 & 0xfff; sy += (w0 >> 12) & 0xfff; st += t0; tm = max(tm, t0); }
