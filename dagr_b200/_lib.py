@@ -7,12 +7,14 @@ src/dagr/graph/ev_graph.cu:9-12).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "libdagr_b200.so"
+# DAGR_B200_LIB points at an alternative build of the same sources (kernel A/B experiments, tools/ab_build.py)
+_LIB_PATH = Path(os.environ["DAGR_B200_LIB"]) if os.environ.get("DAGR_B200_LIB") else _PKG / "libdagr_b200.so"
 _lib = None
 
 ELL = 16
@@ -32,7 +34,7 @@ class Geom(C.Structure):
                 ("nx1", i32), ("ny1", i32),
                 ("CW", i32), ("CH", i32), ("CP", i32),
                 ("NK", i32),
-                ("xkey", p), ("ykey", p), ("spiral", p), ("posx0", p), ("posy0", p), ("vx0", p), ("vy0", p)]
+                ("xkey", p), ("ykey", p), ("spiral", p), ("posx0", p), ("posy0", p), ("vx0", p), ("vy0", p), ("tabx", p), ("taby", p)]
 
 
 class Grid(C.Structure):

@@ -99,7 +99,7 @@ __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p,
 template <bool STAGED>
 __device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, int p, bool active, const int2 me, int eb, int tx0, int ty0,
                                                int TW, int TH, const uint32_t *s_pbin, const uint16_t *s_rng, const uint32_t *s_occ_r,
-                                               const uint32_t *s_occ_c, const int2 *s_ti, const int2 *__restrict__ ti, uint32_t *s_acc,
+                                               const uint32_t *s_occ_c, const short *s_sp2, const int2 *s_ti, const int2 *__restrict__ ti, uint32_t *s_acc,
                                                int32_t *__restrict__ nbr, uint16_t *__restrict__ off, int &n_out)
 {
     const int kmax = g.K - 1;
@@ -119,36 +119,27 @@ __device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, 
         }
     };
     if (n < kmax && ((occr[ty0] >> tx0) & 1u)) visit(ty0 * TW + tx0, 0);   // spiral cell 0: own pixel
+    const int tidx0 = ty0 * TW + tx0;
     for (int d = 1; d <= g.r; d++) {
         if (__all_sync(0xffffffffu, n >= kmax)) break;
-        const uint32_t fm = (2 * d >= 32) ? 0xffffffffu : ((1u << (2 * d)) - 1u);
-        const int cbase = (2 * d - 1) * (2 * d - 1);
-        // leg 0: x = +d, y = -d+1 .. d
-        uint32_t m = (n < kmax) ? ((occc[tx0 + d] >> (ty0 - d + 1)) & fm) : 0u;
-        while (m) {
-            const int i = __ffs(m) - 1; m &= m - 1;
-            visit((ty0 - d + 1 + i) * TW + tx0 + d, cbase + i);
-            if (n >= kmax) m = 0;
+        // one 8d-bit occupancy word per ring, bit i = spiral cell cbase + i (the four legs of spiral.h back to back), so a
+        // lane runs ONE pop loop per ring instead of four: trip counts (popcount of a whole ring) vary much less between
+        // the lanes of a warp than those of single legs
+        const int l2 = 2 * d;
+        const uint32_t fm = (l2 >= 32) ? 0xffffffffu : ((1u << l2) - 1u);
+        const int cbase = (l2 - 1) * (l2 - 1);
+        unsigned long long m = 0;
+        if (n < kmax) {
+            const uint32_t leg0 = (occc[tx0 + d] >> (ty0 - d + 1)) & fm;                          // x = +d, y = -d+1 .. d
+            const uint32_t leg1 = __brev((occr[ty0 + d] >> (tx0 - d)) & fm) >> (32 - l2);         // y = +d, x = d-1 .. -d
+            const uint32_t leg2 = __brev((occc[tx0 - d] >> (ty0 - d)) & fm) >> (32 - l2);         // x = -d, y = d-1 .. -d
+            const uint32_t leg3 = (occr[ty0 - d] >> (tx0 - d + 1)) & fm;                          // y = -d, x = -d+1 .. d
+            m = (unsigned long long)leg0 | ((unsigned long long)leg1 << l2) | ((unsigned long long)leg2 << (2 * l2)) |
+                ((unsigned long long)leg3 << (3 * l2));
         }
-        // leg 1: y = +d, x = d-1 .. -d   (descending: reverse the field)
-        m = (n < kmax) ? (__brev((occr[ty0 + d] >> (tx0 - d)) & fm) >> (32 - 2 * d)) : 0u;
         while (m) {
-            const int i = __ffs(m) - 1; m &= m - 1;
-            visit((ty0 + d) * TW + tx0 + d - 1 - i, cbase + 2 * d + i);
-            if (n >= kmax) m = 0;
-        }
-        // leg 2: x = -d, y = d-1 .. -d
-        m = (n < kmax) ? (__brev((occc[tx0 - d] >> (ty0 - d)) & fm) >> (32 - 2 * d)) : 0u;
-        while (m) {
-            const int i = __ffs(m) - 1; m &= m - 1;
-            visit((ty0 + d - 1 - i) * TW + tx0 - d, cbase + 4 * d + i);
-            if (n >= kmax) m = 0;
-        }
-        // leg 3: y = -d, x = -d+1 .. d
-        m = (n < kmax) ? ((occr[ty0 - d] >> (tx0 - d + 1)) & fm) : 0u;
-        while (m) {
-            const int i = __ffs(m) - 1; m &= m - 1;
-            visit((ty0 - d) * TW + tx0 - d + 1 + i, cbase + 6 * d + i);
+            const int i = __ffsll((long long)m) - 1; m &= m - 1;
+            visit(tidx0 + s_sp2[cbase + i], cbase + i);
             if (n >= kmax) m = 0;
         }
     }
@@ -317,7 +308,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     // bucket(t) = clamp(t/delta_t - (smin-1), 0, NB-1); an event in bucket e needs records of buckets {e-1, e}.
     const int sbase = T.smin - 1;
     bool bucketed = staged && (T.smax - sbase) < BL_NB && (flags == nullptr || flags[0] == 0);   // block-uniform
-    const bool use_rings = TW <= 32 && TH <= 32 && g.r <= 15;           // block-uniform
+    const bool use_rings = TW <= 32 && TH <= 32 && g.r <= 8;            // block-uniform (a ring = 8d <= 64 mask bits)
     for (int pass = 0; pass < 2; pass++) {
         if (use_rings) {
             for (int i = threadIdx.x; i < BL_NB * (TH + TW); i += blockDim.x) s_occ_r[i] = 0u;   // s_occ_c follows s_occ_r
@@ -398,8 +389,8 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         int n;
         const int tidx0 = ty0 * TW + tx0;
         if (use_rings) {
-            if (staged) bl_probe_rings<true>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_ti, ti, s_acc, nbr, off, n);
-            else        bl_probe_rings<false>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_ti, ti, s_acc, nbr, off, n);
+            if (staged) bl_probe_rings<true>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+            else        bl_probe_rings<false>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_sp2, s_ti, ti, s_acc, nbr, off, n);
         } else {
             if (staged) bl_probe<true>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
             else        bl_probe<false>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);

@@ -43,16 +43,8 @@ __device__ __forceinline__ float dec_ordered(uint32_t e)
     return __uint_as_float(u);
 }
 
-// Blackwell packed fp32x2 FMA (SASS FFMA2): d = a*b + c on both halves.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
-{
-    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
-    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
-    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c);
-    unsigned long long rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return *reinterpret_cast<float2 *>(&rd);
-}
+// Blackwell packed fp32x2 FMA (SASS FFMA2): d = a*b + c on both halves (round-to-nearest on each, no cross-talk).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
 // degree-1 open B-spline basis in 2-D (torch_spline_conv semantics): 4 (weight, slot) pairs
 // for pseudo coordinates (ax, ay); kernel_size ks per dim.

@@ -308,8 +308,7 @@ extern "C" int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32
 // finalize pass touch HBM.  Voxels whose neighbourhood exceeds the staging buffer gather from global.
 #define CB2_THREADS 160
 #define CB2_CAP 1344             // staged half-rows (32 B each) per CTA
-#define CB2_G 5                  // spline slots per pass (DAGR_KU = 3 groups of 5)
-#define CB2_NG (DAGR_KU / CB2_G)
+#define CB2_G 5                  // spline slots per pass: one x-slot k, all five y-slots (u = k + 3 j)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -345,65 +344,68 @@ struct CB2Tile {
     int run_start[3], run_len[3], run_off[3];
 };
 
-// One pass = one input-channel half (8 channels) x one group of 5 spline slots of one node:
-//     A_u = sum_{e in N(i) + self} tab[c_e][u] * x_e[half]      (u in the group; 5 x 8 accumulators)
-//     o  += sum_u W_u[half]^T A_u
-// `pass` is warp-uniform, so the phase-2 weights are fetched through the uniform datapath (LDCU) with a
-// run-time offset: one copy of the unrolled FFMA block serves all six passes (instruction-cache friendly),
-// and only 40 accumulators are live (no spills, higher occupancy).
-// s_ell[q][tid] = (row << 12) | spiral cell;  s_tab[g][cell][8] holds the 5 slot weights of group g.
+// One pass = one input-channel half (8 channels) x one x-slot k (the 5 spline slots u = k + 3 j, j = 0..4) of one node:
+//     A_j = sum_{e in N(i) + self} tabx[dx_e][k] * taby[dy_e][j] * x_e[half]      (5 x 8 accumulators)
+//     o  += sum_j W_{k+3j}[half]^T A_j
+// The slot weights are rebuilt from the two per-axis factor tables (2r+1 rows each, geometry.py) instead of a
+// [ncell][16] table: 1.5 KB instead of 21 KB of shared memory per CTA, which is what lets four CTAs share an SM.
+// `half` and `k` are template parameters so the phase-2 weights come through the uniform datapath (LDCU.128);
+// a run-time pass index makes ptxas fetch them with register-indexed LDC, which saturates the ADU pipe.
+// s_ell[q][tid] = (row << 12) | (row swizzle << 11) | (dy + r) << 5 | (dx + r).
+// Variants measured on B200 and rejected (profiles/r01_conv_b_variants.md): 15 slots x 8 channels per pass (120
+// accumulators, 2 CTAs/SM), 15 slots x 4 channels, phase-2 weights from shared memory or half/half.
 template <bool STAGED, int half, int grp>
 __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *__restrict__ xa, const float *s_rows,
-                                         const float *s_tab, const uint32_t *s_ell, const int32_t *__restrict__ nbr,
-                                         const uint16_t *__restrict__ off, const dagr_l1b_params_t &P, int own_row, int ncell,
-                                         float2 o2[8])
+                                         const float *s_wx, const float4 *s_wy, const uint32_t *s_ell, const uint16_t *s_sp,
+                                         const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
+                                         const dagr_l1b_params_t &P, int own_row, int r, float2 o2[8])
 {
     float2 A[CB2_G][4];
 #pragma unroll
     for (int u = 0; u < CB2_G; u++)
 #pragma unroll
         for (int k = 0; k < 4; k++) A[u][k] = make_float2(0.f, 0.f);
-    const float *tabg = s_tab + (size_t)grp * ncell * 8;
 #pragma unroll 2
-    for (int q = -1; q < n; q++) {                                       // q = -1: self loop (spiral cell 0)
-        int row, c, sw;
-        if (q < 0) { row = STAGED ? own_row : p; c = 0; sw = XA_SWZ(p); }
+    for (int q = -1; q < n; q++) {                                       // q = -1: self loop (offset 0,0)
+        int row, sw, dxi, dyi;
+        if (q < 0) { row = STAGED ? own_row : p; sw = XA_SWZ(p); dxi = r; dyi = r; }
         else if (STAGED) {
             const uint32_t ell = s_ell[q * CB2_THREADS + threadIdx.x];
-            row = (int)(ell >> 12); c = (int)(ell & 0x7ff); sw = (int)((ell >> 11) & 1u);
+            row = (int)(ell >> 12); sw = (int)((ell >> 11) & 1u); dxi = (int)(ell & 31u); dyi = (int)((ell >> 5) & 31u);
         } else {
-            row = nbr[(int64_t)q * N + p]; c = off[(int64_t)q * N + p]; sw = XA_SWZ(row);
+            row = nbr[(int64_t)q * N + p]; sw = XA_SWZ(row);
+            const uint32_t d = s_sp[off[(int64_t)q * N + p]];
+            dxi = (int)(d & 31u); dyi = (int)(d >> 5);
         }
         const float4 *src = STAGED ? reinterpret_cast<const float4 *>(s_rows + (int64_t)row * 8)
                                    : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + row) * 8);
         const float4 t0 = src[sw], t1 = src[sw ^ 1];
         const float2 e[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
-        const int ts = 4 * XA_SWZ(c);
-        const float4 w0 = *reinterpret_cast<const float4 *>(tabg + c * 8 + ts);
-        const float w4 = tabg[c * 8 + (ts ^ 4)];
-        const float t[CB2_G] = {w0.x, w0.y, w0.z, w0.w, w4};
+        const float wx = s_wx[dxi * 4 + grp];
+        const float4 wya = s_wy[2 * dyi];
+        const float wy4 = s_wy[2 * dyi + 1].x;
+        const float wy[CB2_G] = {wya.x, wya.y, wya.z, wya.w, wy4};
 #pragma unroll
-        for (int u = 0; u < CB2_G; u++) {
-            const float2 tt = make_float2(t[u], t[u]);
+        for (int j = 0; j < CB2_G; j++) {
+            const float w = __fmul_rn(wy[j], wx);                       // == tab[c][grp + 3 j] bit for bit (geometry.py)
+            const float2 tt = make_float2(w, w);
 #pragma unroll
-            for (int k = 0; k < 4; k++) A[u][k] = ffma2(tt, e[k], A[u][k]);
+            for (int k = 0; k < 4; k++) A[j][k] = ffma2(tt, e[k], A[j][k]);
         }
     }
-    // phase 2.  The weights sit in the constant bank at a run-time (warp-uniform) offset, i.e. every fetch is an LDC
-    // through the address-divergence unit (~1 per 8 cycles per SM): fetch 128 bits at a time and feed two FFMA2 from it.
-    const float (*W)[16][16] = &P.w[grp * CB2_G];
+    // phase 2: weights from the constant bank through uniform 128-bit loads, two FFMA2 per load
 #pragma unroll
-    for (int u = 0; u < CB2_G; u++)
+    for (int j = 0; j < CB2_G; j++)
 #pragma unroll
         for (int k = 0; k < 4; k++)
 #pragma unroll
             for (int c4 = 0; c4 < 4; c4++) {
-                const float4 wa = *reinterpret_cast<const float4 *>(&W[u][8 * half + 2 * k][4 * c4]);
-                const float4 wb = *reinterpret_cast<const float4 *>(&W[u][8 * half + 2 * k + 1][4 * c4]);
-                o2[2 * c4] = ffma2(make_float2(A[u][k].x, A[u][k].x), make_float2(wa.x, wa.y), o2[2 * c4]);
-                o2[2 * c4 + 1] = ffma2(make_float2(A[u][k].x, A[u][k].x), make_float2(wa.z, wa.w), o2[2 * c4 + 1]);
-                o2[2 * c4] = ffma2(make_float2(A[u][k].y, A[u][k].y), make_float2(wb.x, wb.y), o2[2 * c4]);
-                o2[2 * c4 + 1] = ffma2(make_float2(A[u][k].y, A[u][k].y), make_float2(wb.z, wb.w), o2[2 * c4 + 1]);
+                const float4 wa = *reinterpret_cast<const float4 *>(&P.w[grp + 3 * j][8 * half + 2 * k][4 * c4]);
+                const float4 wb = *reinterpret_cast<const float4 *>(&P.w[grp + 3 * j][8 * half + 2 * k + 1][4 * c4]);
+                o2[2 * c4] = ffma2(make_float2(A[j][k].x, A[j][k].x), make_float2(wa.x, wa.y), o2[2 * c4]);
+                o2[2 * c4 + 1] = ffma2(make_float2(A[j][k].x, A[j][k].x), make_float2(wa.z, wa.w), o2[2 * c4 + 1]);
+                o2[2 * c4] = ffma2(make_float2(A[j][k].y, A[j][k].y), make_float2(wb.x, wb.y), o2[2 * c4]);
+                o2[2 * c4 + 1] = ffma2(make_float2(A[j][k].y, A[j][k].y), make_float2(wb.z, wb.w), o2[2 * c4 + 1]);
             }
 }
 
@@ -424,7 +426,7 @@ __device__ __forceinline__ int cb2_round_to_pixel(float mean, int size)
     return min(max(k, 0), size - 1);
 }
 
-__global__ void __launch_bounds__(CB2_THREADS, 3)
+__global__ void __launch_bounds__(CB2_THREADS, 4)
 k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
              const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
              const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off, const float *__restrict__ tab,
@@ -439,8 +441,10 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     __shared__ long long s_sum[CB2_THREADS / 32][3];
     __shared__ int s_tm[CB2_THREADS / 32];
     float *s_rows = (float *)smem_raw;                                   // [CB2_CAP][8]   one channel half of the 3 runs
-    float *s_tab = s_rows + (size_t)CB2_CAP * 8;                         // [CB2_NG][ncell][8]
-    uint32_t *s_ell = (uint32_t *)(s_tab + (size_t)CB2_NG * g.ncell * 8);// [15][CB2_THREADS]
+    float *s_wx = s_rows + (size_t)CB2_CAP * 8;                          // [2r+1][4]   x factor of the slot weights
+    float4 *s_wy = (float4 *)(s_wx + 128);                               // [2r+1][2]   y factor
+    uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [15][CB2_THREADS]
+    uint16_t *s_sp = (uint16_t *)(s_ell + (DAGR_ELL - 1) * CB2_THREADS); // [ncell]  (dx + r) | (dy + r) << 5
     const int cell = blockIdx.x;
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
@@ -451,31 +455,30 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
         if (threadIdx.x < 16) xg[(int64_t)cell * ldx + threadIdx.x] = 0.f;
         return;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // the six run boundaries are independent loads: one lane each, then lane 0 lays the runs out
         const int clo = max(cx - 1, 0), chi = min(cx + 1, g.nx1 - 1);
+        const int lane = threadIdx.x, rr = lane >> 1, ry = cy - 1 + rr;
+        int v = 0;
+        if (lane < 6 && ry >= 0 && ry < g.ny1)
+            v = start[((int64_t)b * per + ry * g.nx1 + ((lane & 1) ? chi + 1 : clo)) * g.CP];
         int o = 0;
-        for (int rr = 0; rr < 3; rr++) {
-            const int ry = cy - 1 + rr;
-            if (ry < 0 || ry >= g.ny1) { T.run_start[rr] = 0; T.run_len[rr] = 0; T.run_off[rr] = o; continue; }
-            const int64_t c0 = (int64_t)b * per + ry * g.nx1 + clo, c1 = (int64_t)b * per + ry * g.nx1 + chi + 1;
-            const int s = start[c0 * g.CP], e = start[c1 * g.CP];
-            T.run_start[rr] = s; T.run_len[rr] = e - s; T.run_off[rr] = o;
-            o += e - s;
-        }
-        mbar_init(&s_bar, 1);
-    }
-    // slot-weight table regrouped as [group][cell][8] (5 used) so one pass reads two aligned vectors per edge
-    for (int i = threadIdx.x; i < g.ncell * 4; i += blockDim.x) {
-        const int c = i >> 2, v = i & 3;
-        const float4 t4 = __ldg(reinterpret_cast<const float4 *>(tab + c * DAGR_TABW) + v);
-        const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int u = v * 4 + k;
-            // same 16-byte chunk swizzle as the xa rows (XA_SWZ) so that random table rows spread over all bank groups
-            if (u < DAGR_KU) s_tab[((size_t)(u / CB2_G) * g.ncell + c) * 8 + (((u % CB2_G) + 4 * XA_SWZ(c)) & 7)] = tv[k];
+        for (int k = 0; k < 3; k++) {
+            const int s0 = __shfl_sync(0xffffffffu, v, 2 * k), e0 = __shfl_sync(0xffffffffu, v, 2 * k + 1);
+            const bool ok = (cy - 1 + k >= 0) && (cy - 1 + k < g.ny1);
+            if (lane == 0) { T.run_start[k] = ok ? s0 : 0; T.run_len[k] = ok ? e0 - s0 : 0; T.run_off[k] = o; }
+            o += ok ? e0 - s0 : 0;
         }
+        if (lane == 0) mbar_init(&s_bar, 1);
     }
+    for (int i = threadIdx.x; i < 2 * g.r + 1; i += blockDim.x) {
+        reinterpret_cast<float4 *>(s_wx)[i] = __ldg(reinterpret_cast<const float4 *>(g.tabx) + i);
+        s_wy[2 * i] = __ldg(reinterpret_cast<const float4 *>(g.taby) + 2 * i);
+        s_wy[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(g.taby) + 2 * i + 1);
+    }
+    for (int i = threadIdx.x; i < g.ncell; i += blockDim.x)
+        s_sp[i] = (uint16_t)(((int)g.spiral[2 * i] + g.r) | (((int)g.spiral[2 * i + 1] + g.r) << 5));
     __syncthreads();
     const int total = T.run_off[2] + T.run_len[2];
     const bool staged = total <= CB2_CAP;                                // block-uniform
@@ -511,7 +514,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             for (int q = 0; q < DAGR_ELL - 1; q++) {
                 const int j = jj[q];
                 const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
-                s_ell[q * CB2_THREADS + threadIdx.x] = ((uint32_t)row << 12) | ((uint32_t)XA_SWZ(j) << 11) | (uint32_t)cc[q];
+                s_ell[q * CB2_THREADS + threadIdx.x] = ((uint32_t)row << 12) | ((uint32_t)XA_SWZ(j) << 11) | (uint32_t)s_sp[cc[q]];
             }
         }
         float2 o2[8];
@@ -550,8 +553,8 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
                 }
 #define CB2_PASS(H, G)                                                                                               \
     do {                                                                                                            \
-        if (staged) cb2_pass<true, H, G>(N, p, n, xa, s_rows, s_tab, s_ell, nbr, off, P, p + d1, g.ncell, o2);      \
-        else        cb2_pass<false, H, G>(N, p, n, xa, s_rows, s_tab, s_ell, nbr, off, P, 0, g.ncell, o2);          \
+        if (staged) cb2_pass<true, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, o2); \
+        else        cb2_pass<false, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, o2);     \
     } while (0)
                 if (half == 0) { CB2_PASS(0, 0); CB2_PASS(0, 1); CB2_PASS(0, 2); }
                 else           { CB2_PASS(1, 0); CB2_PASS(1, 1); CB2_PASS(1, 2); }
@@ -644,8 +647,8 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
 {
     DAGR_CHECK_ARG(g && p_host, "null argument");
     const int cells = g->B * g->ny1 * g->nx1;
-    DAGR_CHECK_ARG(g->ncell <= 2048, "spiral cell index must fit 11 bits");
-    const size_t smem = (size_t)CB2_CAP * 32 + (size_t)CB2_NG * g->ncell * 8 * 4 + (size_t)(DAGR_ELL - 1) * CB2_THREADS * 4;
+    DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
+    const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)(DAGR_ELL - 1) * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     k_l1_conv_b2<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, tab,

@@ -197,6 +197,22 @@ class Geometry:
                 m = slot[:, s] == sl
                 tab[m, u] += basis[m, s]
         self.tab1 = tab
+        # the table is a product: tab[c][k + 3 j] = tabx[dx + r][k] * taby[dy + r][j] (one bilinear factor per axis);
+        # conv_b rebuilds the 15 weights from the two factors (8 floats instead of 16 per edge)
+        cell_of = {(int(dx), int(dy)): c for c, (dx, dy) in enumerate(self.spiral.tolist())}
+        c0 = tab[0, :15].reshape(5, 3)
+        j0, k0 = [int(v) for v in torch.nonzero(c0 == 1.0)[0]]
+        r = self.r
+        tabx = torch.zeros((2 * r + 1, 4), dtype=torch.float32)
+        taby = torch.zeros((2 * r + 1, 8), dtype=torch.float32)
+        for i in range(-r, r + 1):
+            tabx[i + r, :3] = tab[cell_of[(i, 0)], :15].reshape(5, 3)[j0]
+            taby[i + r, :5] = tab[cell_of[(0, i)], :15].reshape(5, 3)[:, k0]
+        dxs, dys = self.spiral[:, 0].long() + r, self.spiral[:, 1].long() + r
+        prod = (taby[dys, :5].unsqueeze(2) * tabx[dxs, :3].unsqueeze(1)).reshape(-1, 15)
+        if not torch.equal(prod, tab[:, :15]):
+            raise ValueError("event-level slot table is not an exact product of per-axis factors")
+        self.tabx, self.taby = tabx, taby
 
         # den for event-level LUT: same expression as init_lut
         self.device = torch.device(device)
@@ -213,6 +229,8 @@ class Geometry:
         self.d_posxr = self.posxr.to(dev)
         self.d_posyr = self.posyr.to(dev)
         self.d_tab1 = self.tab1.to(dev)
+        self.d_tabx = self.tabx.to(dev)
+        self.d_taby = self.taby.to(dev)
         self.d_vx0 = self.vx0.to(dev)
         self.d_vy0 = self.vy0.to(dev)
         g = _lib.Geom()
@@ -226,6 +244,7 @@ class Geometry:
         g.spiral = self.d_spiral.data_ptr()
         g.posx0 = self.d_posx0.data_ptr(); g.posy0 = self.d_posy0.data_ptr()
         g.vx0 = self.d_vx0.data_ptr(); g.vy0 = self.d_vy0.data_ptr()
+        g.tabx = self.d_tabx.data_ptr(); g.taby = self.d_taby.data_ptr()
         self.c_geom = g
         for lv in self.levels:
             gr = _lib.Grid()

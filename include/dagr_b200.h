@@ -52,6 +52,8 @@ typedef struct {
     const float   *posy0;          /* [H]  fl(y / H)                                                 */
     const int32_t *vx0;            /* [nx1+1] first pixel column of each pool1 voxel (vx0[nx1] = W)  */
     const int32_t *vy0;            /* [ny1+1] first pixel row of each pool1 voxel    (vy0[ny1] = H)  */
+    const float   *tabx;           /* [2r+1][4] x factor of the slot weights: tab[c][k+3j] = tabx[dx+r][k]*taby[dy+r][j] */
+    const float   *taby;           /* [2r+1][8] y factor (5 used)                                     */
 } dagr_geom_t;
 
 /* ---------------------------------------------------------------------------------------------
