@@ -67,6 +67,28 @@ class GridState:
         self.x = None
 
 
+class _WsView:
+    """workspace seen by one forward: the event-level buffers are shared, everything the coarse stack touches
+    (zero-on-entry accumulators, grid states, pooled buffers, the captured CUDA graph) belongs to a SLOT so that
+    the coarse stack of step i can run on a side stream while the event-level kernels of step i+1 execute."""
+    _SLOT_KEYS = ("zero_buf", "grids", "pool", "graph", "graph_warm", "graph_key")
+
+    def __init__(self, base: dict, slot: dict):
+        self.base, self.slot = base, slot
+
+    def __getitem__(self, k):
+        return self.slot[k] if k in self._SLOT_KEYS else self.base[k]
+
+    def __setitem__(self, k, v):
+        (self.slot if k in self._SLOT_KEYS else self.base)[k] = v
+
+    def __contains__(self, k):
+        return k in (self.slot if k in self._SLOT_KEYS else self.base)
+
+    def get(self, k, default=None):
+        return (self.slot if k in self._SLOT_KEYS else self.base).get(k, default)
+
+
 class Engine:
     def __init__(self, model):
         self.model = model
@@ -83,6 +105,15 @@ class Engine:
         self.last = {}
         self.launches = 0                    # kernels of libdagr_b200.so enqueued so far
         self.prof = None                     # dict name -> [(start_evt, end_evt)] when per-op timing is on
+        # overlap=True: the coarse stack + NMS of step i run on a side stream (double-buffered hand-off) while the
+        # caller's stream already executes the event-level kernels of step i+1.  Results of a step are then valid only
+        # after join() (or on result_stream()); they stay valid until the second next forward.  Events-only model,
+        # reset=True forwards; everything else silently takes the serial path.
+        self.overlap = False
+        self._cstream = None
+        self._slot = 0
+        self._done = [None, None]
+        self._out_slot = {}
 
     # kernels enqueued by each C-ABI call (see csrc/*.cu)
     _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=1, dagr_l1_x0_image=1, dagr_xa_permute=1, dagr_l1_conv_a_image=1, dagr_voxel_sample_max=1,
@@ -255,6 +286,36 @@ class Engine:
             self._ws[key] = ws
         return ws
 
+    def _slot_view(self, ws: dict, slot: int, geom: Geometry, dev) -> _WsView:
+        slots = ws.setdefault("slots", {})
+        sw = slots.get(slot)
+        if sw is None:
+            if slot == 0:
+                sw = dict(zero_buf=ws["zero_buf"], grids=ws["grids"], pool=ws["pool"])
+            else:
+                sw = dict(zero_buf=torch.zeros_like(ws["zero_buf"]), grids=[GridState(lv, geom.cells(lv), dev) for lv in range(4)],
+                          pool={})
+            slots[slot] = sw
+        return _WsView(ws, sw)
+
+    def join(self):
+        """make the current stream wait for every coarse stack / NMS still running on the side stream."""
+        cur = torch.cuda.current_stream()
+        for ev in self._done:
+            if ev is not None:
+                cur.wait_event(ev)
+
+    def fence(self):
+        """work enqueued on result_stream() after the last forward (a collective, a copy) becomes part of that step."""
+        if self.overlap and self._cstream is not None and self._out_slot:
+            ev = torch.cuda.Event()
+            ev.record(self._cstream)
+            self._done[next(iter(self._out_slot.values()))] = ev
+
+    def result_stream(self):
+        """context manager: the stream on which the last forward's results are produced (current stream if serial)."""
+        return torch.cuda.stream(self._cstream if (self.overlap and self._cstream is not None) else torch.cuda.current_stream())
+
     def _zs(self, ws, name, dtype):
         off, nbytes = ws["zero_slices"][name]
         return ws["zero_buf"][off:off + nbytes].view(dtype)
@@ -355,6 +416,18 @@ class Engine:
         geom = self.geometry(W, H, B, dev)
         pk = self.pack(geom, dev)
         ws = self.workspace(geom, N, dev)
+        ov = bool(self.overlap and stream_state is None and image_feats is None and self.prof is None and self.use_graphs)
+        slot = 0
+        if ov:
+            slot, self._slot = self._slot, self._slot ^ 1
+            if self._cstream is None:
+                # high priority: the small coarse kernels take SM slots as soon as CTAs of the big event-level kernels retire
+                self._cstream = torch.cuda.Stream(device=dev, priority=-1)
+            if self._done[slot] is not None:                 # the coarse stack that last read this slot's hand-off buffers
+                torch.cuda.current_stream().wait_event(self._done[slot])
+        else:
+            self.join()
+        ws = self._slot_view(ws, slot, geom, dev)
         st = _lib.stream_ptr()
         lib = self.lib
         g = C.byref(geom.c_geom)
@@ -488,14 +561,15 @@ class Engine:
 
         # The coarse stack is ~55 small, fixed-shape launches: replay it as ONE CUDA graph (captured on the second
         # call with identical buffers; the event-level kernels stay eager because their grids depend on N).
-        gkey = (id(ws), id(pk), B, kto, cellmask.data_ptr())
-        if self.use_graphs and self.prof is None and not use_image:
-            cached = ws.get("graph")
-            if cached is not None and cached[0] == gkey:
-                cached[1].replay()
-                self.launches += cached[3]
-                out, grids, inter, dense_all = cached[2]
-            else:
+        gkey = (id(ws.base), slot, id(pk), B, kto, cellmask.data_ptr())
+
+        def run_coarse():
+            if self.use_graphs and self.prof is None and not use_image:
+                cached = ws.get("graph")
+                if cached is not None and cached[0] == gkey:
+                    cached[1].replay()
+                    self.launches += cached[3]
+                    return cached[2]
                 l0 = self.launches
                 res = coarse(_lib.stream_ptr())                          # eager: also allocates every pool buffer
                 nk = self.launches - l0
@@ -503,14 +577,29 @@ class Engine:
                 if ws["graph_warm"] >= 2 and ws.get("graph_key") == gkey:
                     torch.cuda.synchronize()
                     gr = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(gr):
+                    # kernel nodes inherit the priority of the CAPTURE stream: capture on the high-priority side stream in
+                    # overlap mode so the small coarse kernels get SM slots while a big event-level kernel is resident
+                    with torch.cuda.graph(gr, stream=self._cstream if ov else None):
                         res_c = coarse(_lib.stream_ptr())
                     self.launches -= nk                                  # capture enqueues nothing
                     ws["graph"] = (gkey, gr, res_c, nk)
                 ws["graph_key"] = gkey
-                out, grids, inter, dense_all = res
+                return res
+            return coarse(st)
+
+        if ov:
+            fine_done = torch.cuda.Event()
+            fine_done.record()
+            with torch.cuda.stream(self._cstream):
+                self._cstream.wait_event(fine_done)
+                out, grids, inter, dense_all = run_coarse()
+                ev = torch.cuda.Event()
+                ev.record()
+            self._done[slot] = ev
+            self._out_slot = {out.data_ptr(): slot}
         else:
-            out, grids, inter, dense_all = coarse(st)
+            out, grids, inter, dense_all = run_coarse()
+            self._out_slot = {}
         g1, g2, g3, g4 = grids
         self.last = dict(geom=geom, ws=ws, N=N, grids=[g1, g2, g3, g4], inter=inter, dense=dense_all, x1=x1)
         return out
@@ -532,11 +621,23 @@ class Engine:
         B, A, D = decoded.shape
         nc = D - 5
         dev = decoded.device
-        det = torch.empty((B, A, 6), dtype=torch.float32, device=dev)
-        ndet = torch.empty(B, dtype=torch.int32, device=dev)
-        self._run("postprocess_nms", self.lib.dagr_postprocess_nms, _lib.ptr(decoded), B, A, nc, float(conf_thre), float(nms_thre), int(width),
-                                                 int(height), 1 if filtering else 0, _lib.ptr(det), _lib.ptr(ndet),
-                                                 _lib.stream_ptr())
+        slot = self._out_slot.get(decoded.data_ptr()) if self.overlap else None
+        if slot is None:
+            det = torch.empty((B, A, 6), dtype=torch.float32, device=dev)
+            ndet = torch.empty(B, dtype=torch.int32, device=dev)
+            self._run("postprocess_nms", self.lib.dagr_postprocess_nms, _lib.ptr(decoded), B, A, nc, float(conf_thre), float(nms_thre),
+                      int(width), int(height), 1 if filtering else 0, _lib.ptr(det), _lib.ptr(ndet), _lib.stream_ptr())
+            return det, ndet
+        # overlapped forward: NMS follows the coarse stack on the side stream, into per-slot result buffers
+        sw = self.last["ws"]
+        det = self._buf(sw, "post_det", (B, A, 6), torch.float32, dev)
+        ndet = self._buf(sw, "post_ndet", (B,), torch.int32, dev)
+        with torch.cuda.stream(self._cstream):
+            self._run("postprocess_nms", self.lib.dagr_postprocess_nms, _lib.ptr(decoded), B, A, nc, float(conf_thre), float(nms_thre),
+                      int(width), int(height), 1 if filtering else 0, _lib.ptr(det), _lib.ptr(ndet), _lib.stream_ptr())
+            ev = torch.cuda.Event()
+            ev.record()
+        self._done[slot] = ev
         return det, ndet
 
     # ------------------------------------------------------------------------------------------

@@ -214,6 +214,7 @@ class DAGR(YOLOX):
         outputs = self.forward_decoded(x, reset=reset)
         det, ndet = self.engine.postprocess(outputs, self.conf_threshold, self.nms_threshold, self.width, self.height,
                                             filtering=filtering)
+        self.engine.join()                                           # overlap mode: results come from the side stream
         counts = ndet.tolist()                                       # the one device->host sync of the forward
         detections = []
         for b, n in enumerate(counts):
