@@ -270,7 +270,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     torch.manual_seed(0)
     model = randomize_bn(DAGR(margs, height=H, width=W).eval()).to(dev)
     eng = model.engine
@@ -410,8 +421,13 @@ def main():
     cb_ms = (prof.get("l1_conv_b_pool_voxel") or prof.get("l1_conv_b_pool") or dict(ms=float("nan")))["ms"]
     ach = cb_bytes / (cb_ms * 1e-3) / 1e9
     cb_flops = 2.0 * (E * 15 * 16 + N * (15 * 256 + 256 + 48))          # slot form actually executed
+    traffic = None
+    try:                                                   # per-launch DRAM bytes of this kernel from the committed ncu capture
+        traffic = json.load(open(ROOT / "profiles" / "ncu_traffic.json"))["k_l1_conv_b2"]["dram_bytes"]
+    except Exception:
+        pass
     roofline = dict(kernel="k_l1_conv_b2 (fused SplineConv 16->16 + BN + skip + act + pool1 max/mean/round, TMA-staged, one CTA per voxel)", bound="hbm",
-                    achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                    achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=cb_bytes, launch_ms=cb_ms, share_of_step=cb_ms / tot_ms,
                     fp32_tflops=cb_flops / (cb_ms * 1e-3) / 1e12, mean_degree=E / max(N, 1),
                     step_algorithmic_bytes=N * 320 + 40 * (E - N) + 0, step_frac=(N * 320 + 40 * E) / (ms * 1e-3) / 1e9 / peak,
