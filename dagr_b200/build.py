@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libdagr_b200.so"
-SOURCES = ["capi.cu", "graph.cu", "build_l1.cu", "conv_l1.cu", "image_l1.cu", "coarse.cu", "masked.cu"]
+SOURCES = ["capi.cu", "graph.cu", "build_l1.cu", "conv_l1.cu", "image_l1.cu", "coarse.cu", "masked.cu", "ingest.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -26,6 +26,10 @@ void dagr_set_error(const char *fmt, ...);
 
 static inline int dagr_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// exclusive prefix sum of n ints (graph.cu); blocksums: int[dagr_scan_blocks(n) + 2]; the grand total is left in
+// blocksums[dagr_scan_blocks(n)]
+int scan_exclusive(const int *in, int *out, int64_t n, int *blocksums, cudaStream_t st);
+
 // xa rows are stored half-major [2][N][8]; inside each 32-byte half-row the two 16-byte chunks are swapped when bit 2 of
 // the row index is set.  A staged copy of the rows (TMA keeps them contiguous) then spreads a warp's random row gathers
 // over all eight 16-byte bank groups instead of four (LDS.128 conflict degree ~3.4 -> ~2.3).

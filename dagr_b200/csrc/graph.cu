@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int *__restri
 }
 
 // out[0..n-1] = exclusive prefix of in, out[n] = total.  blocksums: dagr_scan_blocks(n)+1 ints.
-static int scan_exclusive(const int *in, int *out, int64_t n, int *blocksums, cudaStream_t st)
+int scan_exclusive(const int *in, int *out, int64_t n, int *blocksums, cudaStream_t st)
 {
     int64_t nb = dagr_scan_blocks(n);
     if (nb == 0) nb = 1;

@@ -132,4 +132,5 @@ def synth_batch(batch_size: int, n_events: int, width: int = 640, height: int = 
               num_graphs=batch_size)
     if with_image:
         kw["image"] = torch.randint(0, 256, (batch_size, 3, height, width), generator=g, dtype=torch.uint8)
+    kw["dims"] = (int(width), int(height), int(time_window))      # host copy of width/height/time_window: no device read per forward
     return EventBatch(**kw)

@@ -164,8 +164,12 @@ class DAGR(YOLOX):
         dev = x.pos.device
         if dev.type != "cuda":
             raise RuntimeError("dagr_b200: DAGR.forward needs CUDA tensors (there is no CPU fallback)")
-        W, H = int(x.width[0]), int(x.height[0])
-        T = int(x.time_window[0]) if hasattr(x, "time_window") else self.time_window
+        dims = getattr(x, "dims", None)                     # host-side (W, H, T) when the batch carries it: no sync
+        if dims is not None:
+            W, H, T = (int(v) for v in dims)
+        else:
+            W, H = int(x.width[0]), int(x.height[0])
+            T = int(x.time_window[0]) if hasattr(x, "time_window") else self.time_window
         if getattr(x, "batch", None) is None:
             x.batch = torch.zeros(len(x.pos), dtype=torch.long, device=dev)
         N = int(x.pos.shape[0])

@@ -289,6 +289,34 @@ int dagr_masked_inplace_bn(const int64_t *idx, int64_t K, const float *x, float 
 int dagr_masked_isdiff(int64_t *idx_inout, int64_t K, const float *a, const float *b, int C, float atol,
                        float rtol, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Event ingest on the device: what the reference does on the CPU between the raw DSEC stream and
+ * the graph builder.
+ *
+ *   dagr_downsample_events : scripts/downsample_events.py:91-124 (downsample_events + the numba loop
+ *       _filter_events_resize).  x,y u16[N] at the input resolution, p i8[N] in {-1,+1}, events in time order;
+ *       fx = int(in_w/out_w), fy = int(in_h/out_h); change_map f32[out_h*out_w] is the per-output-pixel accumulator that
+ *       the script carries from chunk to chunk (in/out).  mask u8[N] (out) = 1 where the event passes.
+ *       work: cell,tmp,sorted i32[N]; count i32[out_h*out_w] (MUST be zero on entry; is zero again on exit);
+ *       start i32[out_h*out_w+1]; blocksums i32[dagr_scan_blocks(max(N, out_h*out_w))+2].
+ *   dagr_compact_events   : events[mask] with x/fx, y/fy as (x / fx).astype(uint16) (:102-104); order preserved.
+ *       work: flag i32[N], pos i32[N+1]; n_out i32[1] (device) = number kept.
+ *   dagr_ingest_events    : one sample: keep t < t_cut (dsec_data.py:177-179) and y < H (:142-143), t = T + t - t[-1] of
+ *       the kept events (:144-145), polarity 2p-1 when p_is_01 (:146), int16/int32 casts (data/utils.py:12-13), fp32
+ *       normalisation by [W,H,T] (utils/buffers.py:41-43) and denormalisation (ev_tgn.py:15-16) -> batch i32[M] (= sample),
+ *       pos i32[M,3], polarity f32[M]: the inputs of dagr_graph_sort.  work: flag i32[N], pos i32[N+1], tlast u64[1].
+ * ------------------------------------------------------------------------------------------- */
+int dagr_downsample_events(const uint16_t *x, const uint16_t *y, const int8_t *p, int64_t N, int fx, int fy,
+                           int out_w, int out_h, float *change_map, int32_t *cell, int32_t *tmp, int32_t *sorted,
+                           int32_t *count, int32_t *start, int32_t *blocksums, uint8_t *mask, void *stream);
+int dagr_compact_events(const uint8_t *mask, int64_t N, const uint16_t *x, const uint16_t *y, const int64_t *t,
+                        const int8_t *p, int fx, int fy, int32_t *flag, int32_t *pos, int32_t *blocksums,
+                        uint16_t *xo, uint16_t *yo, int64_t *to, int8_t *po, int32_t *n_out, void *stream);
+int dagr_ingest_events(const uint16_t *x, const uint16_t *y, const int64_t *t, const int8_t *p, int64_t N,
+                       int p_is_01, int W, int H, int T, int64_t t_cut, int sample, int32_t *flag, int32_t *pos,
+                       int32_t *blocksums, unsigned long long *tlast, int32_t *batch_out, int32_t *pos_out,
+                       float *feat_out, int32_t *n_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

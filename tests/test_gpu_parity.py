@@ -564,3 +564,75 @@ def test_masked_ops_vs_oracle_and_reference():
     if ext is not None:
         r2 = ext.masked_isdiff(idx.clone(), a, c, 1e-8, 1e-5)
         assert torch.equal(mine, r2.cpu())
+
+
+def test_ingest_downsampler_vs_reference_golden_and_oracle():
+    """csrc/ingest.cu vs (a) the golden vectors made by the reference's own numba down-sampler, chunk by chunk with the
+    change map carried over, and (b) the oracle on a larger random stream with hot pixels; bit-exact (mask, coordinates,
+    accumulator map)."""
+    from dagr_b200 import ingest
+    from oracle import ref_ingest as R
+    g = np.load(ROOT / "tests" / "golden" / "downsample_golden.npz")
+    for case in range(3):
+        iw, ih, ow, oh = (int(v) for v in g[f"c{case}_shape"])
+        cm = None
+        for k in range(3):
+            ev = {q: torch.from_numpy(g[f"c{case}_k{k}_in_{q}"].astype({"x": "int16", "y": "int16", "p": "int8", "t": "int64"}[q])).cuda()
+                  for q in "xypt"}
+            out, cm = ingest.downsample_events(ev, ih, iw, oh, ow, change_map=cm)
+            for q in "xypt":
+                assert np.array_equal(out[q].cpu().numpy().astype("int64"), g[f"c{case}_k{k}_out_{q}"].astype("int64")), (case, k, q)
+            assert np.array_equal(cm.cpu().numpy(), g[f"c{case}_k{k}_map"])
+    rng = np.random.default_rng(11)
+    n, iw, ih, ow, oh = 300000, 640, 480, 320, 240
+    ev = dict(x=rng.integers(0, iw, n).astype("int16"), y=rng.integers(0, ih, n).astype("int16"),
+              p=(2 * rng.integers(0, 2, n) - 1).astype("int8"), t=np.sort(rng.integers(0, 50000, n)).astype("int64"))
+    ev["x"][:20000] = 101; ev["y"][:20000] = 57; ev["p"][:20000:4] = 1          # one very hot pixel block
+    want, wm = R.downsample_events({k: v.astype("uint16") if k in "xy" else v for k, v in ev.items()}, ih, iw, oh, ow)
+    got, gm = ingest.downsample_events({k: torch.from_numpy(v).cuda() for k, v in ev.items()}, ih, iw, oh, ow)
+    for q in "xypt":
+        assert np.array_equal(got[q].cpu().numpy().astype("int64"), want[q].astype("int64")), q
+    assert np.array_equal(gm.cpu().numpy(), wm)
+    empty, cm0 = ingest.downsample_events({k: torch.from_numpy(v[:0]).cuda() for k, v in ev.items()}, ih, iw, oh, ow)
+    assert all(v.numel() == 0 for v in empty.values()) and float(cm0.abs().sum()) == 0.0
+
+
+def test_ingest_window_vs_oracle_and_forward():
+    """raw (x, y, t, p) -> batch/pos_denorm/polarity on the device equals the oracle's restatement of
+    preprocess_events + to_data + format_data + denormalize_pos, and the collated batch drives DAGR.forward to the same
+    detections as the formatted float batch."""
+    from dagr_b200 import ingest
+    from dagr_b200.data import EventBatch, format_data
+    from oracle import ref_ingest as R
+    W, H, T, B = 320, 215, 1_000_000, 2
+    rng = np.random.default_rng(5)
+    samples, raw = [], []
+    for b in range(B):
+        n = 9000 + 1000 * b
+        ev = dict(x=rng.integers(0, W, n).astype("int16"), y=rng.integers(0, 240, n).astype("int16"),
+                  t=np.sort(rng.integers(7_000_000, 7_060_000, n)).astype("int64"), p=rng.integers(0, 2, n).astype("int8"))
+        cut = 7_050_000
+        den, pol = R.preprocess_window({k: v.astype("uint16") if k in "xy" else v for k, v in ev.items()}, W, H, T, t_cut=cut)
+        bt, pos, feat = ingest.ingest_window({k: torch.from_numpy(v).cuda() for k, v in ev.items()}, W, H, T, t_cut=cut, sample=b)
+        assert np.array_equal(pos.cpu().numpy(), den) and np.array_equal(feat.cpu().numpy(), pol)
+        assert int(bt.min()) == b and int(bt.max()) == b
+        samples.append((bt, pos, feat))
+        keep = (ev["t"] < cut) & (ev["y"] < H)
+        t_rel = T + ev["t"][keep] - ev["t"][keep][-1]                    # dsec_data.py:145, before any float round trip
+        raw.append((np.stack([ev["x"][keep], ev["y"][keep], t_rel], axis=1), pol))
+    e0 = ingest.ingest_window({k: torch.zeros(0, dtype=torch.int64, device="cuda") for k in "xytp"}, W, H, T)
+    assert e0[1].shape == (0, 3)
+    model, args = make_model("s", H, W)
+    model.cuda()
+    d_int = ingest.collate(samples, W, H, T)
+    det_int = model(d_int)[0]
+    # the same events through the reference's float interface (format_data on int16 pos + int32 t)
+    pos16 = torch.from_numpy(np.concatenate([r[0][:, :2] for r in raw]).astype("int16"))
+    t32 = torch.from_numpy(np.concatenate([r[0][:, 2] for r in raw]).astype("int32"))
+    dflt = EventBatch(x=torch.from_numpy(np.concatenate([r[1] for r in raw])).view(-1, 1), pos=pos16, t=t32,
+                      batch=torch.cat([s[0] for s in samples]).long().cpu(), width=torch.full((B,), W), height=torch.full((B,), H),
+                      time_window=torch.full((B,), T), num_graphs=B)
+    det_f = model(format_data(dflt).cuda())[0]
+    for a, b_ in zip(det_int, det_f):
+        assert a["boxes"].shape == b_["boxes"].shape
+        assert_close(a["boxes"].cpu(), b_["boxes"].cpu(), what="boxes (ingest vs float batch)")

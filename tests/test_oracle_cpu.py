@@ -278,3 +278,39 @@ def test_oracle_reproduces_committed_golden_forward():
     assert torch.equal(o["edge_index"].int(), fix["edge_index"])
     assert torch.allclose(o["decoded"], fix["decoded"], rtol=1e-6, atol=1e-6)
     assert [len(d["boxes"]) for d in o["detections"]] == fix["n_det"]
+
+
+def test_ingest_oracle_vs_reference_golden():
+    """oracle/ref_ingest.py against tests/golden/downsample_golden.npz, which was produced by the reference's own numba
+    down-sampler (scripts/downsample_events.py:91-124) with the change map carried over three chunks."""
+    import numpy as np
+    from pathlib import Path
+    from oracle import ref_ingest as R
+    g = np.load(Path(__file__).parent / "golden" / "downsample_golden.npz")
+    for case in range(3):
+        iw, ih, ow, oh = (int(v) for v in g[f"c{case}_shape"])
+        cm = None
+        for k in range(3):
+            ev = {q: g[f"c{case}_k{k}_in_{q}"] for q in "xypt"}
+            out, cm = R.downsample_events(ev, ih, iw, oh, ow, change_map=cm)
+            for q in "xypt":
+                assert np.array_equal(out[q], g[f"c{case}_k{k}_out_{q}"]), (case, k, q)
+            assert np.array_equal(cm, g[f"c{case}_k{k}_map"])
+
+
+def test_ingest_window_oracle_identities():
+    """dsec_data.py:141-147 + format/denormalise round trip: crop, window cut, t relative to the last kept event."""
+    import numpy as np
+    from oracle import ref_ingest as R
+    rng = np.random.default_rng(3)
+    n, W, H, T = 4000, 640, 430, 1_000_000
+    ev = dict(x=rng.integers(0, W, n).astype("uint16"), y=rng.integers(0, 480, n).astype("uint16"),
+              t=np.sort(rng.integers(10_000_000, 10_050_000, n)).astype("int64"), p=rng.integers(0, 2, n).astype("uint8"))
+    den, pol = R.preprocess_window(ev, W, H, T, t_cut=10_040_000)
+    keep = (ev["t"] < 10_040_000) & (ev["y"] < H)
+    assert len(den) == int(keep.sum()) and set(np.unique(pol)) <= {-1.0, 1.0}
+    assert np.array_equal(den[:, 0], ev["x"][keep]) and np.array_equal(den[:, 1], ev["y"][keep])
+    t_rel = T + ev["t"][keep] - ev["t"][keep][-1]
+    assert np.all(np.abs(den[:, 2] - t_rel) <= 1) and den[-1, 2] in (T, T - 1)       # fp32 round trip may lose 1 us
+    den0, pol0 = R.preprocess_window({k: v[:0] for k, v in ev.items()}, W, H, T)
+    assert den0.shape == (0, 3) and pol0.shape == (0,)
