@@ -354,11 +354,11 @@ struct CB2Tile {
 // s_ell[q][tid] = (row << 12) | (row swizzle << 11) | (dy + r) << 5 | (dx + r).
 // Variants measured on B200 and rejected (profiles/r01_conv_b_variants.md): 15 slots x 8 channels per pass (120
 // accumulators, 2 CTAs/SM), 15 slots x 4 channels, phase-2 weights from shared memory or half/half.
-template <bool STAGED, int half, int grp>
+template <bool STAGED, int half, int grp, class PT>
 __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *__restrict__ xa, const float *s_rows,
                                          const float *s_wx, const float4 *s_wy, const uint32_t *s_ell, const uint16_t *s_sp,
                                          const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
-                                         const dagr_l1b_params_t &P, int own_row, int r, float2 o2[8])
+                                         const PT &P, int own_row, int r, float2 o2[8])
 {
     float2 A[CB2_G][4];
 #pragma unroll
@@ -426,13 +426,19 @@ __device__ __forceinline__ int cb2_round_to_pixel(float mean, int size)
     return min(max(k, 0), size - 1);
 }
 
-__global__ void __launch_bounds__(CB2_THREADS, 4)
+// The kernel is a template over the input rows: <dagr_l1b_params_t, 2, false> is conv_block2 (16 channels = 2 staged
+// 8-channel chunks, skip + act + pool1 epilogue); <dagr_l1img_params_t, 3, true> is the image-fusion variant of
+// conv_block1.conv_block1 (1 + 16 + 2 input channels padded to 3 chunks; epilogue = BN + act, rows written back
+// chunk-major for conv_block2, plus the layer's skip branch BN(Linear(x0)) -> skip_out; no pooling).
+template <class PT, int NCH, bool MODE_A>
+__global__ void __launch_bounds__(CB2_THREADS, MODE_A ? 3 : 4)
 k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
              const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
              const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off, const float *__restrict__ tab,
-             const __grid_constant__ dagr_l1b_params_t P, const float *__restrict__ skip_pre, const int min_idx,
+             const __grid_constant__ PT P, const float *__restrict__ skip_pre, const int min_idx,
              float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
-             float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx)
+             float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx,
+             float *__restrict__ xa_out, float *__restrict__ skip_out)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ CB2Tile T;
@@ -451,6 +457,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
     const int nown = p1 - p0;
     if (nown == 0) {                                                     // block-uniform
+        if (MODE_A) return;
         if (threadIdx.x == 0) { cnt[cell] = 0; pxy[2 * cell] = 0; pxy[2 * cell + 1] = 0; tmean[cell] = 0.f; tmax[cell] = 0.f; }
         if (threadIdx.x < 16) xg[(int64_t)cell * ldx + threadIdx.x] = 0.f;
         return;
@@ -517,11 +524,13 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
                 s_ell[q * CB2_THREADS + threadIdx.x] = ((uint32_t)row << 12) | ((uint32_t)XA_SWZ(j) << 11) | (uint32_t)s_sp[cc[q]];
             }
         }
-        float2 o2[8];
+        float2 o2[8], sk2[MODE_A ? 8 : 1];
 #pragma unroll
         for (int k = 0; k < 8; k++) o2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < (MODE_A ? 8 : 1); k++) sk2[k] = make_float2(0.f, 0.f);
 #pragma unroll 1
-        for (int half = 0; half < 2; half++) {
+        for (int half = 0; half < NCH; half++) {
             if (staged) {
                 __syncthreads();                                        // everyone is done with the previous half's rows
                 if (threadIdx.x == 0) {
@@ -549,6 +558,11 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
                             const float4 w4 = *reinterpret_cast<const float4 *>(&P.root[8 * half + k][4 * c4]);
                             o2[2 * c4] = ffma2(make_float2(v[k], v[k]), make_float2(w4.x, w4.y), o2[2 * c4]);
                             o2[2 * c4 + 1] = ffma2(make_float2(v[k], v[k]), make_float2(w4.z, w4.w), o2[2 * c4 + 1]);
+                            if constexpr (MODE_A) {                      // the layer's skip branch Linear(x0) (conv.py:41-52)
+                                const float4 k4 = *reinterpret_cast<const float4 *>(&P.skip[8 * half + k][4 * c4]);
+                                sk2[2 * c4] = ffma2(make_float2(v[k], v[k]), make_float2(k4.x, k4.y), sk2[2 * c4]);
+                                sk2[2 * c4 + 1] = ffma2(make_float2(v[k], v[k]), make_float2(k4.z, k4.w), sk2[2 * c4 + 1]);
+                            }
                         }
                 }
 #define CB2_PASS(H, G)                                                                                               \
@@ -556,16 +570,41 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
         if (staged) cb2_pass<true, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, o2); \
         else        cb2_pass<false, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, o2);     \
     } while (0)
-                if (half == 0) { CB2_PASS(0, 0); CB2_PASS(0, 1); CB2_PASS(0, 2); }
-                else           { CB2_PASS(1, 0); CB2_PASS(1, 1); CB2_PASS(1, 2); }
+                if (half == 0)      { CB2_PASS(0, 0); CB2_PASS(0, 1); CB2_PASS(0, 2); }
+                else if (half == 1) { CB2_PASS(1, 0); CB2_PASS(1, 1); CB2_PASS(1, 2); }
+                else if constexpr (NCH > 2) { CB2_PASS(2, 0); CB2_PASS(2, 1); CB2_PASS(2, 2); }
 #undef CB2_PASS
             }
         }
-        if (inrange) { const uint32_t w0 = xyb[p]; const int t0 = ti[p].x; sx += w0 & 0xfff; sy += (w0 >> 12) & 0xfff; st += t0; tm = max(tm, t0); }
+        if (!MODE_A && inrange) { const uint32_t w0 = xyb[p]; const int t0 = ti[p].x; sx += w0 & 0xfff; sy += (w0 >> 12) & 0xfff; st += t0; tm = max(tm, t0); }
         if (!active) continue;
         float o[16];
 #pragma unroll
         for (int c = 0; c < 8; c++) { o[2 * c] = o2[c].x; o[2 * c + 1] = o2[c].y; }
+        if constexpr (MODE_A) {
+            float sk[16];
+#pragma unroll
+            for (int c = 0; c < 8; c++) { sk[2 * c] = sk2[c].x; sk[2 * c + 1] = sk2[c].y; }
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const float r = fmaf(o[c], P.scale[c], P.shift[c]);
+                o[c] = P.relu ? fmaxf(r, 0.f) : r;
+                sk[c] = fmaf(sk[c], P.sscale[c], P.sshift[c]);
+            }
+            const int sw = XA_SWZ(p);
+            float4 *dst = reinterpret_cast<float4 *>(xa_out + (int64_t)p * 8);
+            dst[sw] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[sw ^ 1] = make_float4(o[4], o[5], o[6], o[7]);
+            dst = reinterpret_cast<float4 *>(xa_out + (N + (int64_t)p) * 8);
+            dst[sw] = make_float4(o[8], o[9], o[10], o[11]);
+            dst[sw ^ 1] = make_float4(o[12], o[13], o[14], o[15]);
+            float4 *sd = reinterpret_cast<float4 *>(skip_out + (int64_t)p * 16);
+            sd[0] = make_float4(sk[0], sk[1], sk[2], sk[3]);
+            sd[1] = make_float4(sk[4], sk[5], sk[6], sk[7]);
+            sd[2] = make_float4(sk[8], sk[9], sk[10], sk[11]);
+            sd[3] = make_float4(sk[12], sk[13], sk[14], sk[15]);
+            continue;
+        }
         const uint32_t wxy = xyb[p];
         const int x = wxy & 0xfff, y = (wxy >> 12) & 0xfff;
         float skv[16];
@@ -599,6 +638,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             dst[3] = make_float4(o[12], o[13], o[14], o[15]);
         }
     }
+    if (MODE_A) return;
     // ---- pool1: per-voxel max / mean position (pooling.py:66-86) -------------------------------------
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -649,10 +689,31 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
     const int cells = g->B * g->ny1 * g->nx1;
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
     const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)(DAGR_ELL - 1) * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
-    DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    k_l1_conv_b2<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, tab,
-                                                                     *p_host, skip_pre, min_idx, persist, x1, cnt, pxy, tmean, tmax, xg, ldx);
+    auto kern = k_l1_conv_b2<dagr_l1b_params_t, 2, false>;
+    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, tab, *p_host,
+                                                              skip_pre, min_idx, persist, x1, cnt, pxy, tmean, tmax, xg, ldx,
+                                                              nullptr, nullptr);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
+// image fusion: conv_block1.conv_block1 on the 19-channel rows x0 (chunk-major [3][N][8], chunks swizzled like xa)
+extern "C" int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const float *x0, const int32_t *nbr,
+                                    const uint16_t *off, const dagr_l1img_params_t *p_host, float *xa, float *skipv, void *stream)
+{
+    DAGR_CHECK_ARG(g && p_host, "null argument");
+    if (N <= 0) return DAGR_OK;
+    const int cells = g->B * g->ny1 * g->nx1;
+    DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
+    const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)(DAGR_ELL - 1) * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
+    auto kern = k_l1_conv_b2<dagr_l1img_params_t, 3, true>;
+    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, nullptr, nullptr, nullptr, x0, nbr, off, nullptr, *p_host,
+                                                              nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                              nullptr, 0, xa, skipv);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

@@ -49,7 +49,8 @@ __device__ __forceinline__ float bilin_sample(const float *__restrict__ img, int
     return acc;
 }
 
-// x0[chunk][p][8]: [pol, f0..f15, x/W, y/H, 0 x5]
+// x0[chunk][p][8]: [pol, f0..f15, x/W, y/H, 0 x5]; the two 16-byte halves of a row are swapped when XA_SWZ(p), like xa,
+// so that the staged conv kernel (conv_l1.cu) reads both with the same row addressing
 __global__ void k_l1_x0_image(const dagr_geom_t g, int64_t N, const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s,
                               const float *__restrict__ img0, int h, int w, float *__restrict__ x0)
 {
@@ -62,6 +63,7 @@ __global__ void k_l1_x0_image(const dagr_geom_t g, int64_t N, const uint32_t *__
     const int x = wd & 0xfff, y = (wd >> 12) & 0xfff, b = wd >> 24;
     const float px = g.posx0[x], py = g.posy0[y];
     const Bilin bl = bilin_setup(px, py, b, (float)g.W, (float)g.H, g.B, h, w);
+    const int sw4 = 4 * XA_SWZ(p);
     float f[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) f[k] = bilin_sample(img0, g.B, 16, h, w, 4 * q + k, bl);
@@ -69,14 +71,14 @@ __global__ void k_l1_x0_image(const dagr_geom_t g, int64_t N, const uint32_t *__
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int ch = 1 + 4 * q + k;
-        x0[((int64_t)(ch >> 3) * N + p) * 8 + (ch & 7)] = f[k];
+        x0[((int64_t)(ch >> 3) * N + p) * 8 + ((ch & 7) ^ sw4)] = f[k];
     }
     if (q == 0) {
-        x0[p * 8] = feat_s[p];
-        x0[((int64_t)2 * N + p) * 8 + 1] = px;
-        x0[((int64_t)2 * N + p) * 8 + 2] = py;
+        x0[p * 8 + (0 ^ sw4)] = feat_s[p];
+        x0[((int64_t)2 * N + p) * 8 + (1 ^ sw4)] = px;
+        x0[((int64_t)2 * N + p) * 8 + (2 ^ sw4)] = py;
 #pragma unroll
-        for (int k = 3; k < 8; k++) x0[((int64_t)2 * N + p) * 8 + k] = 0.f;
+        for (int k = 3; k < 8; k++) x0[((int64_t)2 * N + p) * 8 + (k ^ sw4)] = 0.f;
     }
 }
 
@@ -90,125 +92,87 @@ extern "C" int dagr_l1_x0_image(const dagr_geom_t *g, int64_t N, const uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv_block1.conv_block1 with 19 (padded 24) input channels: thread per node, 3 channel chunks x 3 slot
-// groups = 9 passes over the ELL row (global gathers: this variant is bounded by the ResNet trunk anyway).
+// per-voxel max of image features sampled at the voxel's events (net.py:128-131 before pool1): one CTA per voxel.
+// All events of a voxel sample a small window of the feature map (voxel extent x map/sensor scale, + 1), so the window
+// of both batch planes the trilinear sample can touch is staged in shared memory once ([z][y][x][C], channels
+// innermost -> conflict-free), and every (event, channel) sample reads shared memory only.  The tap order and the
+// fp32 arithmetic are those of bilin_sample, i.e. of the oracle.  Windows that do not fit fall back to global taps.
 // ------------------------------------------------------------------------------------------------
-#define CI_THREADS 128
-#define CI_G 5
+#define VS_THREADS 128
+#define VS_SMEM_FLOATS 10240                                            // 40 KB: e.g. 2 planes x 6 x 6 x 128 channels
 
-__global__ void __launch_bounds__(CI_THREADS)
-k_l1_conv_a_image(const dagr_geom_t g, int64_t N, const float *__restrict__ x0, const int32_t *__restrict__ nbr,
-                  const uint16_t *__restrict__ off, const float *__restrict__ tab, const dagr_l1img_params_t *__restrict__ P,
-                  float *__restrict__ xa, float *__restrict__ skipv)
+template <bool STAGED>
+__device__ __forceinline__ float vs_sample(const float *__restrict__ img, const float *s_patch, int Bi, int C, int h, int w,
+                                           int c, const Bilin &q, int zb, int yb, int xb, int ph, int pw)
 {
-    extern __shared__ __align__(16) float s_tab[];                      // [3][ncell][8]
-    for (int i = threadIdx.x; i < g.ncell * DAGR_TABW; i += blockDim.x) {
-        const int c = i / DAGR_TABW, u = i % DAGR_TABW;
-        if (u < DAGR_KU) s_tab[((size_t)(u / CI_G) * g.ncell + c) * 8 + (u % CI_G)] = tab[i];
-    }
-    __syncthreads();
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    const int n = nbr[(int64_t)(DAGR_ELL - 1) * N + p];
-    float o[16], sk[16];
+    float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; k++) { o[k] = 0.f; sk[k] = 0.f; }
-#pragma unroll 1
-    for (int ch = 0; ch < 3; ch++) {
-        {   // root + skip on this chunk of x_i
-            const float4 *src = reinterpret_cast<const float4 *>(x0 + ((int64_t)ch * N + p) * 8);
-            const float4 t0 = src[0], t1 = src[1];
-            const float v[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    for (int dz = 0; dz < 2; dz++) {
+        const int z = q.z0 + dz;
+        const float wz = dz ? q.tz : 1.f - q.tz;
+        if (z < 0 || z >= Bi) continue;
 #pragma unroll
-            for (int k = 0; k < 8; k++)
+        for (int dy = 0; dy < 2; dy++) {
+            const int y = q.y0 + dy;
+            const float wy = dy ? q.ty : 1.f - q.ty;
+            if (y < 0 || y >= h) continue;
 #pragma unroll
-                for (int c = 0; c < 16; c++) {
-                    o[c] = fmaf(v[k], P->root[8 * ch + k][c], o[c]);
-                    sk[c] = fmaf(v[k], P->skip[8 * ch + k][c], sk[c]);
-                }
-        }
-#pragma unroll 1
-        for (int grp = 0; grp < 3; grp++) {
-            float A[CI_G][8];
-#pragma unroll
-            for (int u = 0; u < CI_G; u++)
-#pragma unroll
-                for (int k = 0; k < 8; k++) A[u][k] = 0.f;
-            const float *tabg = s_tab + (size_t)grp * g.ncell * 8;
-            for (int q = -1; q < n; q++) {
-                const int row = q < 0 ? (int)p : nbr[(int64_t)q * N + p];
-                const int c = q < 0 ? 0 : (int)off[(int64_t)q * N + p];
-                const float4 *src = reinterpret_cast<const float4 *>(x0 + ((int64_t)ch * N + row) * 8);
-                const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
-                const float e[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                const float4 w0 = *reinterpret_cast<const float4 *>(tabg + c * 8);
-                const float t[CI_G] = {w0.x, w0.y, w0.z, w0.w, tabg[c * 8 + 4]};
-#pragma unroll
-                for (int u = 0; u < CI_G; u++)
-#pragma unroll
-                    for (int k = 0; k < 8; k++) A[u][k] = fmaf(t[u], e[k], A[u][k]);
+            for (int dx = 0; dx < 2; dx++) {
+                const int x = q.x0 + dx;
+                const float wx = dx ? q.tx : 1.f - q.tx;
+                if (x < 0 || x >= w) continue;
+                const float v = STAGED ? s_patch[(((z - zb) * ph + (y - yb)) * pw + (x - xb)) * C + c]
+                                       : __ldg(img + (((int64_t)z * C + c) * h + y) * w + x);
+                acc += v * (wx * wy * wz);
             }
-#pragma unroll
-            for (int u = 0; u < CI_G; u++)
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-#pragma unroll
-                    for (int c = 0; c < 16; c++) o[c] = fmaf(A[u][k], P->w[grp * CI_G + u][8 * ch + k][c], o[c]);
         }
     }
-#pragma unroll
-    for (int c = 0; c < 16; c++) {
-        const float r = fmaf(o[c], P->scale[c], P->shift[c]);
-        o[c] = P->relu ? fmaxf(r, 0.f) : r;
-        sk[c] = fmaf(sk[c], P->sscale[c], P->sshift[c]);
-    }
-    const int sw = XA_SWZ(p);
-    float4 *dst = reinterpret_cast<float4 *>(xa + p * 8);
-    dst[sw] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[sw ^ 1] = make_float4(o[4], o[5], o[6], o[7]);
-    dst = reinterpret_cast<float4 *>(xa + (N + p) * 8);
-    dst[sw] = make_float4(o[8], o[9], o[10], o[11]);
-    dst[sw ^ 1] = make_float4(o[12], o[13], o[14], o[15]);
-    float4 *sd = reinterpret_cast<float4 *>(skipv + p * 16);
-    sd[0] = make_float4(sk[0], sk[1], sk[2], sk[3]);
-    sd[1] = make_float4(sk[4], sk[5], sk[6], sk[7]);
-    sd[2] = make_float4(sk[8], sk[9], sk[10], sk[11]);
-    sd[3] = make_float4(sk[12], sk[13], sk[14], sk[15]);
+    return acc;
 }
 
-extern "C" int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const float *x0, const int32_t *nbr, const uint16_t *off,
-                                    const float *tab, const dagr_l1img_params_t *p_dev, float *xa, float *skipv, void *stream)
-{
-    DAGR_CHECK_ARG(g && p_dev, "null argument");
-    if (N <= 0) return DAGR_OK;
-    const size_t smem = (size_t)3 * g->ncell * 8 * sizeof(float);
-    DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_a_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_l1_conv_a_image<<<dagr_div_up(N, CI_THREADS), CI_THREADS, smem, (cudaStream_t)stream>>>(*g, N, x0, nbr, off, tab, p_dev, xa, skipv);
-    DAGR_CHECK_LAUNCH();
-    return DAGR_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// per-voxel max of image features sampled at the voxel's events: one CTA per voxel, lanes over channels
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(VS_THREADS)
 k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
                    const float *__restrict__ img, int C, int h, int w, float *__restrict__ xg, int ldx, int c0)
 {
-    __shared__ float s_m[4][128];
+    __shared__ float s_m[VS_THREADS / 32][128];
+    __shared__ float s_patch[VS_SMEM_FLOATS];
     const int cell = blockIdx.x;
+    const int per = g.ny1 * g.nx1;
+    const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
     const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (p1 == p0) {                                                       // block-uniform
+        for (int c = threadIdx.x; c < C; c += blockDim.x) xg[(int64_t)cell * ldx + c0 + c] = 0.f;
+        return;
+    }
+    // window of the map this voxel's pixels can touch: the sample coordinates are monotone in x / y, so the corner
+    // pixels bound it (same arithmetic as the per-event set-up)
+    const Bilin lo = bilin_setup(g.posx0[g.vx0[cx]], g.posy0[g.vy0[cy]], b, (float)g.W, (float)g.H, g.B, h, w);
+    const Bilin hi = bilin_setup(g.posx0[g.vx0[cx + 1] - 1], g.posy0[g.vy0[cy + 1] - 1], b, (float)g.W, (float)g.H, g.B, h, w);
+    const int xb = max(lo.x0, 0), yb = max(lo.y0, 0), zb = max(lo.z0, 0);
+    const int xe = min(hi.x0 + 1, w - 1), ye = min(hi.y0 + 1, h - 1), ze = min(lo.z0 + 1, g.B - 1);
+    const int pw = xe - xb + 1, ph = ye - yb + 1, pz = ze - zb + 1;
+    const bool staged = pw > 0 && ph > 0 && pz > 0 && (int64_t)pz * ph * pw * C <= VS_SMEM_FLOATS;   // block-uniform
+    if (staged) {
+        const int tot = pz * ph * pw * C;
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+            const int x = i % pw, r1 = i / pw, y = r1 % ph, r2 = r1 / ph, c = r2 % C, z = r2 / C;          // x fastest: coalesced
+            s_patch[((z * ph + y) * pw + x) * C + c] = __ldg(img + (((int64_t)(zb + z) * C + c) * h + yb + y) * w + xb + x);
+        }
+        __syncthreads();
+    }
     for (int cb = 0; cb < C; cb += 128) {
         float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int p = p0 + wid; p < p1; p += 4) {
+        for (int p = p0 + wid; p < p1; p += VS_THREADS / 32) {
             const uint32_t wd = xyb[p];
-            const int x = wd & 0xfff, y = (wd >> 12) & 0xfff, b = wd >> 24;
+            const int x = wd & 0xfff, y = (wd >> 12) & 0xfff;
             const Bilin bl = bilin_setup(g.posx0[x], g.posy0[y], b, (float)g.W, (float)g.H, g.B, h, w);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int c = cb + lane + 32 * k;
-                if (c < C) m[k] = fmaxf(m[k], bilin_sample(img, g.B, C, h, w, c, bl));
+                if (c < C)
+                    m[k] = fmaxf(m[k], staged ? vs_sample<true>(img, s_patch, g.B, C, h, w, c, bl, zb, yb, xb, ph, pw)
+                                              : vs_sample<false>(img, s_patch, g.B, C, h, w, c, bl, zb, yb, xb, ph, pw));
             }
         }
 #pragma unroll
@@ -216,8 +180,9 @@ k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const
         __syncthreads();
         const int c = cb + threadIdx.x;
         if (c < C) {
-            float v = fmaxf(fmaxf(s_m[0][threadIdx.x], s_m[1][threadIdx.x]), fmaxf(s_m[2][threadIdx.x], s_m[3][threadIdx.x]));
-            xg[(int64_t)cell * ldx + c0 + c] = (p1 > p0) ? v : 0.f;
+            float v = s_m[0][threadIdx.x];
+            for (int w2 = 1; w2 < VS_THREADS / 32; w2++) v = fmaxf(v, s_m[w2][threadIdx.x]);
+            xg[(int64_t)cell * ldx + c0 + c] = v;
         }
         __syncthreads();
     }
@@ -228,7 +193,7 @@ extern "C" int dagr_voxel_sample_max(const dagr_geom_t *g, int64_t N, const int3
 {
     (void)N;
     const int cells = g->B * g->ny1 * g->nx1;
-    k_voxel_sample_max<<<cells, 128, 0, (cudaStream_t)stream>>>(*g, start, xyb, img, C, h, w, xg, ldx, c0);
+    k_voxel_sample_max<<<cells, VS_THREADS, 0, (cudaStream_t)stream>>>(*g, start, xyb, img, C, h, w, xg, ldx, c0);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

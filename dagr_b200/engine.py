@@ -213,8 +213,7 @@ class Engine:
             s, b = _fold_bn(ca.norm); _fill(pi.scale, s); _fill(pi.shift, b)
             s, b = _fold_bn(cb.norm_skip); _fill(pi.sscale, s); _fill(pi.sshift, b)
             pi.relu = 1
-            raw = (C.c_char * C.sizeof(pi)).from_buffer(pi)
-            pk["l1img"] = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+            pk["l1img"] = pi
         pk["layers"] = [_LayerPack(getattr(bb, n), relu, device) for n in ("layer2", "layer3", "layer4", "layer5")]
         heads = []
         for k in range(hd.num_scales):
@@ -463,8 +462,8 @@ class Engine:
             skipv = self._buf(ws, "skipv", (max(N, 1), 16), torch.float32, dev)
             self._run("l1_x0_image", lib.dagr_l1_x0_image, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(f0),
                       int(f0.shape[2]), int(f0.shape[3]), _lib.ptr(x0), st)
-            self._run("l1_conv_a_image", lib.dagr_l1_conv_a_image, g, N, _lib.ptr(x0), _lib.ptr(nbr), _lib.ptr(off),
-                      _lib.ptr(geom.d_tab1), _lib.ptr(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), st)
+            self._run("l1_conv_a_image", lib.dagr_l1_conv_a_image, g, N, _lib.ptr(ws["start"]), _lib.ptr(x0), _lib.ptr(nbr), _lib.ptr(off),
+                      C.byref(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), st)
         elif self.fused_build or stream_state is not None:
             if min_idx > 0:
                 self._run("xa_gather", lib.dagr_xa_permute, N, _lib.ptr(ws["perm"]), min_idx, _lib.ptr(ws["xa"]),

@@ -128,11 +128,12 @@ typedef struct {
     int32_t relu;
 } dagr_l1img_params_t;
 
-/* conv_block1.conv_block1 on 19 input channels -> xa (half-major [2][N][8]) and the layer's skip branch
- * skipv f32[N,16] = BN(Linear(x0)) consumed by dagr_l1_conv_b_pool_voxel(skip_pre) */
-int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const float *x0, const int32_t *nbr, const uint16_t *off,
-                         const float *tab, const dagr_l1img_params_t *p_dev /* DEVICE copy (26 KB) */, float *xa, float *skipv,
-                         void *stream);
+/* conv_block1.conv_block1 on 19 input channels (x0 chunk-major [3][N][8] from dagr_l1_x0_image) -> xa (half-major
+ * [2][N][8]) and the layer's skip branch skipv f32[N,16] = BN(Linear(x0)) consumed by dagr_l1_conv_b_pool_voxel(skip_pre).
+ * Same one-CTA-per-voxel, TMA-staged kernel as conv_block2 (template instance with 3 input chunks). */
+int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const float *x0, const int32_t *nbr,
+                         const uint16_t *off, const dagr_l1img_params_t *p_host /* passed by value to the kernel (26 KB) */,
+                         float *xa, float *skipv, void *stream);
 
 /* per-voxel channel max of image features sampled at the voxel's events (sampling_skip before pool1,
  * net.py:128-131): xg[cell*ldx + c0 + c], c < C, empty voxels -> 0 */
