@@ -135,7 +135,7 @@ k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const
                    const float *__restrict__ img, int C, int h, int w, float *__restrict__ xg, int ldx, int c0)
 {
     __shared__ float s_m[VS_THREADS / 32][128];
-    __shared__ float s_patch[VS_SMEM_FLOATS];
+    __shared__ __align__(16) float s_patch[VS_SMEM_FLOATS];
     const int cell = blockIdx.x;
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
@@ -160,6 +160,67 @@ k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const
             s_patch[((z * ph + y) * pw + x) * C + c] = __ldg(img + (((int64_t)(zb + z) * C + c) * h + yb + y) * w + xb + x);
         }
         __syncthreads();
+    }
+    // fast path: C/8 lanes per event (8 channels = two 16-byte shared loads per tap and lane), 32/(C/8) events per warp;
+    // the 8 trilinear tap weights are computed once per lane and reused for its 8 channels
+    const int lpe = C >> 3;                                               // lanes per event
+    if (staged && (C & 7) == 0 && C <= 128 && lpe >= 1 && (lpe & (lpe - 1)) == 0) {          // block-uniform
+        const int epw = 32 / lpe, sub = lane / lpe, cl = (lane % lpe) * 8;
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) m[k] = -INFINITY;
+        for (int pb = p0 + wid * epw; pb < p1; pb += (VS_THREADS / 32) * epw) {
+            const int p = pb + sub;
+            if (p < p1) {
+                const uint32_t wd = xyb[p];
+                const int x = wd & 0xfff, y = (wd >> 12) & 0xfff;
+                const Bilin q = bilin_setup(g.posx0[x], g.posy0[y], b, (float)g.W, (float)g.H, g.B, h, w);
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] = 0.f;
+#pragma unroll
+                for (int dz = 0; dz < 2; dz++) {
+                    const int z = q.z0 + dz;
+                    const float wz = dz ? q.tz : 1.f - q.tz;
+                    if (z < 0 || z >= g.B) continue;
+#pragma unroll
+                    for (int dy = 0; dy < 2; dy++) {
+                        const int yy = q.y0 + dy;
+                        const float wy = dy ? q.ty : 1.f - q.ty;
+                        if (yy < 0 || yy >= h) continue;
+#pragma unroll
+                        for (int dx = 0; dx < 2; dx++) {
+                            const int xx = q.x0 + dx;
+                            const float wx = dx ? q.tx : 1.f - q.tx;
+                            if (xx < 0 || xx >= w) continue;
+                            const float wgt = wx * wy * wz;                 // same association as bilin_sample
+                            const float4 *src = reinterpret_cast<const float4 *>(s_patch + (((z - zb) * ph + (yy - yb)) * pw + (xx - xb)) * C + cl);
+                            const float4 v0 = src[0], v1 = src[1];
+                            acc[0] += v0.x * wgt; acc[1] += v0.y * wgt; acc[2] += v0.z * wgt; acc[3] += v0.w * wgt;
+                            acc[4] += v1.x * wgt; acc[5] += v1.y * wgt; acc[6] += v1.z * wgt; acc[7] += v1.w * wgt;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], acc[k]);
+            }
+        }
+        // lanes with the same channel block sit lpe apart
+        for (int d = lpe; d < 32; d <<= 1)
+#pragma unroll
+            for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], __shfl_xor_sync(0xffffffffu, m[k], d));
+        float *s_mm = &s_m[0][0];                                          // [warps][128]
+        if (lane < lpe) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s_mm[wid * 128 + cl + k] = m[k];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float v = s_mm[c];
+            for (int w2 = 1; w2 < VS_THREADS / 32; w2++) v = fmaxf(v, s_mm[w2 * 128 + c]);
+            xg[(int64_t)cell * ldx + c0 + c] = v;
+        }
+        return;
     }
     for (int cb = 0; cb < C; cb += 128) {
         float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
