@@ -358,7 +358,7 @@ template <bool STAGED, int half, int grp, class PT>
 __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *__restrict__ xa, const float *s_rows,
                                          const float *s_wx, const float4 *s_wy, const uint32_t *s_ell, const uint16_t *s_sp,
                                          const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
-                                         const PT &P, int own_row, int r, float2 o2[8])
+                                         const PT &P, int own_row, int r, int tix, float2 o2[8])
 {
     float2 A[CB2_G][4];
 #pragma unroll
@@ -370,7 +370,7 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
         int row, sw, dxi, dyi;
         if (q < 0) { row = STAGED ? own_row : p; sw = XA_SWZ(p); dxi = r; dyi = r; }
         else if (STAGED) {
-            const uint32_t ell = s_ell[q * CB2_THREADS + threadIdx.x];
+            const uint32_t ell = s_ell[q * CB2_THREADS + tix];
             row = (int)(ell >> 12); sw = (int)((ell >> 11) & 1u); dxi = (int)(ell & 31u); dyi = (int)((ell >> 5) & 31u);
         } else {
             row = nbr[(int64_t)q * N + p]; sw = XA_SWZ(row);
@@ -499,9 +499,18 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     long long sx = 0, sy = 0, st = 0;
     int tm = -2147483647;
     uint32_t parity = 0;
+    // Sparse voxels (at most one warp of nodes, e.g. the early windows of an inter-frame sequence): the per-thread chain of
+    // six passes is the whole run time of the CTA and four of its five warps would idle.  Warps 0..2 then share the SAME
+    // nodes and take one x-slot each (both channel halves), their partial sums are added through shared memory: a third of
+    // the serial work per thread.  Block-uniform; the dense path below is unchanged.
+    // (compiled into the image-fusion instance only: in the 2-chunk conv_block2 instance the extra live state costs the
+    // dense path 1.3 % and the sparse gain is small, measured)
+    const bool sparse = MODE_A && staged && nown <= 32 && min_idx <= 0;
+    const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5;
     for (int pb0 = p0; pb0 < p1; pb0 += blockDim.x) {
-        const int p = pb0 + threadIdx.x;
-        const bool inrange = p < p1;
+        const int p = sparse ? p0 + lane_ : pb0 + threadIdx.x;
+        const bool inrange = sparse ? (p < p1 && wid_ < 3) : (p < p1);
+        const int tix = sparse ? lane_ : (int)threadIdx.x;                // column of this node in s_ell
         // incremental mode: only new nodes are convolved (the arrival index is only looked at then)
         const bool active = inrange && (min_idx <= 0 || ti[p].y >= min_idx);
         if (min_idx > 0 && !__syncthreads_or(active)) {                  // block-uniform: nothing new in this chunk
@@ -510,7 +519,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
         }
         const int n = active ? nbr[(int64_t)(DAGR_ELL - 1) * N + p] : 0;
         // stage this node's ELL row (independent loads -> one global latency); neighbour positions become staged rows
-        if (staged && active) {
+        if (staged && active && (!sparse || wid_ == 0)) {
             int jj[DAGR_ELL - 1]; int cc[DAGR_ELL - 1];
 #pragma unroll
             for (int q = 0; q < DAGR_ELL - 1; q++) {
@@ -521,7 +530,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             for (int q = 0; q < DAGR_ELL - 1; q++) {
                 const int j = jj[q];
                 const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
-                s_ell[q * CB2_THREADS + threadIdx.x] = ((uint32_t)row << 12) | ((uint32_t)XA_SWZ(j) << 11) | (uint32_t)s_sp[cc[q]];
+                s_ell[q * CB2_THREADS + tix] = ((uint32_t)row << 12) | ((uint32_t)XA_SWZ(j) << 11) | (uint32_t)s_sp[cc[q]];
             }
         }
         float2 o2[8], sk2[MODE_A ? 8 : 1];
@@ -546,7 +555,7 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             }
             if (active) {
                 // root weight on this half of x_i
-                {
+                if (!sparse || wid_ == 0) {
                     const float4 *src = staged ? reinterpret_cast<const float4 *>(s_rows + (int64_t)(p + d1) * 8)
                                                : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + p) * 8);
                     const float4 t0 = src[XA_SWZ(p)], t1 = src[XA_SWZ(p) ^ 1];
@@ -567,17 +576,50 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
                 }
 #define CB2_PASS(H, G)                                                                                               \
     do {                                                                                                            \
-        if (staged) cb2_pass<true, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, o2); \
-        else        cb2_pass<false, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, o2);     \
+        if (staged) cb2_pass<true, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2); \
+        else        cb2_pass<false, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, tix, o2);     \
     } while (0)
-                if (half == 0)      { CB2_PASS(0, 0); CB2_PASS(0, 1); CB2_PASS(0, 2); }
-                else if (half == 1) { CB2_PASS(1, 0); CB2_PASS(1, 1); CB2_PASS(1, 2); }
-                else if constexpr (NCH > 2) { CB2_PASS(2, 0); CB2_PASS(2, 1); CB2_PASS(2, 2); }
+#define CB2_HALF(H)                                                                                                  \
+    do {                                                                                                            \
+        if (!sparse) { CB2_PASS(H, 0); CB2_PASS(H, 1); CB2_PASS(H, 2); }                                            \
+        else if (wid_ == 0) CB2_PASS(H, 0);                                                                         \
+        else if (wid_ == 1) CB2_PASS(H, 1);                                                                         \
+        else CB2_PASS(H, 2);                                                                                        \
+    } while (0)
+                if (half == 0)      CB2_HALF(0);
+                else if (half == 1) CB2_HALF(1);
+                else if constexpr (NCH > 2) CB2_HALF(2);
+#undef CB2_HALF
 #undef CB2_PASS
             }
         }
-        if (!MODE_A && inrange) { const uint32_t w0 = xyb[p]; const int t0 = ti[p].x; sx += w0 & 0xfff; sy += (w0 >> 12) & 0xfff; st += t0; tm = max(tm, t0); }
-        if (!active) continue;
+        if (sparse) {
+            // add the partial sums of warps 1 and 2 (x-slots 1 and 2) to warp 0's: the staged rows are dead by now
+            __syncthreads();
+            float *s_part = s_rows;                                         // [2][32][16]
+            if (active && wid_ >= 1) {
+                float4 *dst = reinterpret_cast<float4 *>(s_part + ((size_t)(wid_ - 1) * 32 + lane_) * 16);
+                dst[0] = make_float4(o2[0].x, o2[0].y, o2[1].x, o2[1].y);
+                dst[1] = make_float4(o2[2].x, o2[2].y, o2[3].x, o2[3].y);
+                dst[2] = make_float4(o2[4].x, o2[4].y, o2[5].x, o2[5].y);
+                dst[3] = make_float4(o2[6].x, o2[6].y, o2[7].x, o2[7].y);
+            }
+            __syncthreads();
+            if (active && wid_ == 0) {
+#pragma unroll
+                for (int w2 = 0; w2 < 2; w2++) {
+                    const float4 *src = reinterpret_cast<const float4 *>(s_part + ((size_t)w2 * 32 + lane_) * 16);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float4 v = src[k];
+                        o2[2 * k].x += v.x; o2[2 * k].y += v.y; o2[2 * k + 1].x += v.z; o2[2 * k + 1].y += v.w;
+                    }
+                }
+            }
+        }
+        const bool owner = !sparse || wid_ == 0;                            // the thread that finishes this node
+        if (!MODE_A && inrange && owner) { const uint32_t w0 = xyb[p]; const int t0 = ti[p].x; sx += w0 & 0xfff; sy += (w0 >> 12) & 0xfff; st += t0; tm = max(tm, t0); }
+        if (!active || !owner) continue;
         float o[16];
 #pragma unroll
         for (int c = 0; c < 8; c++) { o[2 * c] = o2[c].x; o[2 * c + 1] = o2[c].y; }
