@@ -171,6 +171,8 @@ class Engine:
         key = (self._params_key(), tuple(geom.slots1), str(device))
         if self._pack is not None and self._pack_key == key:
             return self._pack
+        if self._cstream is not None:
+            self._cstream.synchronize()                      # a coarse stack in flight may still read the old weight tensors
         m = self.model
         bb, hd = m.backbone, m.head
         act = getattr(m.args, "activation", "relu")
@@ -235,6 +237,10 @@ class Engine:
         ws = self._ws.get(key)
         cap = 0 if ws is None else ws["cap"]
         if ws is None or N > cap:
+            if self._cstream is not None:
+                # the old buffers may still be read by a coarse stack on the side stream; they were allocated on the
+                # caller's stream, so the caching allocator would hand them out again without waiting for that stream
+                self._cstream.synchronize()
             cap = max(int(N * 1.25), 1024)
             dev = device
             nscan = max(geom.NK + 1, cap + 1)
