@@ -166,7 +166,8 @@ typedef struct {
     float scale[16], shift[16];   /* norm                                            */
     float sscale[16], sshift[16]; /* norm_skip                                       */
     int32_t relu;
-    /* slot u = 3*j + i is spline kernel xs[i] + 5*ys[j]; basis evaluated in-kernel at attr = d/den + 0.5 */
+    /* slot u = 3*j + i is spline kernel xs[i] + 5*ys[j].  xs/ys/den describe the slot grid to tools; the kernels take
+     * the basis weights from the host-built tables (geometry.py), never from in-kernel divisions (slower, measured) */
     int32_t xs[3], ys[5];
     float den_x, den_y;           /* fl32(2*M*W), fl32(2*M*H)  (spline_conv.py:28-29) */
 } dagr_l1b_params_t;
@@ -185,7 +186,12 @@ int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, co
 /* Production form of conv_b: one CTA per pool1 voxel; the xa rows of the voxel's 3x3 neighbourhood (three
  * contiguous runs in cell-major order) are staged in shared memory with TMA bulk copies (cp.async.bulk
  * + mbarrier) and pool1 is finished in the same CTA (replaces dagr_l1_conv_b_pool + dagr_pool1_finalize):
- * -> cnt i32[cells], pxy i32[cells,2], tmean/tmax f32[cells], xg f32[cells,16]; x1 optional as above. */
+ * -> cnt i32[cells], pxy i32[cells,2], tmean/tmax f32[cells], xg f32[cells*ldx] (16 channels at column 0); x1 optional
+ * as above.  The per-edge slot weights come from the per-axis factor tables g->tabx / g->taby; `tab` is not read by this
+ * kernel any more (kept in the signature for ABI stability, may be NULL).  skip_pre f32[N,16] (optional): the layer's skip
+ * branch if it was produced elsewhere (image fusion), else it is computed from (polarity, x/W, y/H).  min_idx > 0:
+ * incremental step, only nodes with arrival index >= min_idx are convolved and `persist` f32[cells,16] carries the
+ * running per-voxel max between steps. */
 int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
                               const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
                               const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
