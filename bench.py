@@ -243,6 +243,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
+        config["overlap"] = "n/a (CPU arm)"
         from dagr_b200.model.dagr import DAGR
         torch.manual_seed(0)
         model = randomize_bn(DAGR(margs, height=H, width=W).eval())
