@@ -422,6 +422,8 @@ def main():
     cb_ms = (prof.get("l1_conv_b_pool_voxel") or prof.get("l1_conv_b_pool") or dict(ms=float("nan")))["ms"]
     ach = cb_bytes / (cb_ms * 1e-3) / 1e9
     cb_flops = 2.0 * (E * 15 * 16 + N * (15 * 256 + 256 + 48))          # slot form actually executed
+    clk_ghz = (sampler.summary().get("sm_mhz") or 1965) / 1e3
+    fp32_peak = 148 * 4 * 32 * 2 * 2 / 2 * clk_ghz / 1e3                  # TFLOP/s (the kernel also has an fp32 bound)
     traffic = None
     try:                                                   # per-launch DRAM bytes of this kernel from the committed ncu capture
         traffic = json.load(open(ROOT / "profiles" / "ncu_traffic.json"))["k_l1_conv_b2"]["dram_bytes"]
@@ -430,7 +432,10 @@ def main():
     roofline = dict(kernel="k_l1_conv_b2 (fused SplineConv 16->16 + BN + skip + act + pool1 max/mean/round, TMA-staged, one CTA per voxel)", bound="hbm",
                     achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=cb_bytes, launch_ms=cb_ms, share_of_step=cb_ms / tot_ms,
-                    fp32_tflops=cb_flops / (cb_ms * 1e-3) / 1e12, mean_degree=E / max(N, 1),
+                    fp32_tflops=cb_flops / (cb_ms * 1e-3) / 1e12, fp32_peak_tflops=fp32_peak, fp32_frac=cb_flops / (cb_ms * 1e-3) / 1e12 / fp32_peak,
+                    fp32_peak_source="148 SMs x 4 SMSPs x 32 lanes x 2 FMA (packed FFMA2) x 2 flop, one warp instruction per 2 cycles per SMSP "
+                                     "(B300_MICROARCH.md pipe rates), at the SM clock sampled during the run",
+                    mean_degree=E / max(N, 1),
                     step_algorithmic_bytes=N * 320 + 40 * (E - N) + 0, step_frac=(N * 320 + 40 * E) / (ms * 1e-3) / 1e9 / peak,
                     per_op_ms={k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])})
 
