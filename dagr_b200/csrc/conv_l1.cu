@@ -308,6 +308,7 @@ extern "C" int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32
 // finalize pass touch HBM.  Voxels whose neighbourhood exceeds the staging buffer gather from global.
 #define CB2_THREADS 160
 #define CB2_CAP 1344             // staged half-rows (32 B each) per CTA
+static_assert(2 * CB2_CAP <= 4096, "the ELL word keeps 2*row+swizzle in 12 bits");
 #define CB2_G 5                  // spline slots per pass: one x-slot k, all five y-slots (u = k + 3 j)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -351,7 +352,7 @@ struct CB2Tile {
 // [ncell][16] table: 1.5 KB instead of 21 KB of shared memory per CTA, which is what lets four CTAs share an SM.
 // `half` and `k` are template parameters so the phase-2 weights come through the uniform datapath (LDCU.128);
 // a run-time pass index makes ptxas fetch them with register-indexed LDC, which saturates the ADU pipe.
-// s_ell[q][tid] = (row << 12) | (row swizzle << 11) | (dy + r) << 5 | (dx + r).
+// s_ell[q][tid]: see the staged loop below (byte offsets of the row chunks and of the two factor-table rows).
 // Variants measured on B200 and rejected (profiles/r01_conv_b_variants.md): 15 slots x 8 channels per pass (120
 // accumulators, 2 CTAs/SM), 15 slots x 4 channels, phase-2 weights from shared memory or half/half.
 template <bool STAGED, int half, int grp, class PT>
@@ -365,34 +366,53 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
     for (int u = 0; u < CB2_G; u++)
 #pragma unroll
         for (int k = 0; k < 4; k++) A[u][k] = make_float2(0.f, 0.f);
+#define CB2_EDGE_FMA()                                                                                              \
+    do {                                                                                                            \
+        const float2 e[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)}; \
+        const float wy[CB2_G] = {wya.x, wya.y, wya.z, wya.w, wy4};                                                  \
+        _Pragma("unroll") for (int j = 0; j < CB2_G; j++) {                                                         \
+            const float w = __fmul_rn(wy[j], wx);           /* == tab[c][grp + 3 j] bit for bit (geometry.py) */    \
+            const float2 tt = make_float2(w, w);                                                                    \
+            _Pragma("unroll") for (int k = 0; k < 4; k++) A[j][k] = ffma2(tt, e[k], A[j][k]);                       \
+        }                                                                                                           \
+    } while (0)
+    if constexpr (STAGED) {
+        // the ELL word carries ready-made BYTE offsets: bits 4..15 = 16 * (2 * row + row swizzle) (first 16-byte chunk of
+        // the staged half-row; the other chunk is that offset ^ 16), bits 16..20 = dx + r, bits 21..25 = dy + r.  Slot 0 is
+        // the self loop.  The integer pipe issues at half rate like the FMA pipe, so every shift/mask/add saved per edge
+        // and pass counts as much as an FFMA2.
+        const char *rb = reinterpret_cast<const char *>(s_rows);
+        const char *wxb = reinterpret_cast<const char *>(s_wx) + 4 * grp, *wyb = reinterpret_cast<const char *>(s_wy);
 #pragma unroll 2
-    for (int q = -1; q < n; q++) {                                       // q = -1: self loop (offset 0,0)
-        int row, sw, dxi, dyi;
-        if (q < 0) { row = STAGED ? own_row : p; sw = XA_SWZ(p); dxi = r; dyi = r; }
-        else if (STAGED) {
+        for (int q = 0; q <= n; q++) {
             const uint32_t ell = s_ell[q * CB2_THREADS + tix];
-            row = (int)(ell >> 12); sw = (int)((ell >> 11) & 1u); dxi = (int)(ell & 31u); dyi = (int)((ell >> 5) & 31u);
-        } else {
-            row = nbr[(int64_t)q * N + p]; sw = XA_SWZ(row);
-            const uint32_t d = s_sp[off[(int64_t)q * N + p]];
-            dxi = (int)(d & 31u); dyi = (int)(d >> 5);
+            const uint32_t ro = ell & 0xfff0u, xo = (ell >> 12) & 0x1f0u, yo = (ell >> 16) & 0x3e0u;
+            const float4 t0 = *reinterpret_cast<const float4 *>(rb + ro), t1 = *reinterpret_cast<const float4 *>(rb + (ro ^ 16u));
+            const float wx = *reinterpret_cast<const float *>(wxb + xo);
+            const float4 wya = *reinterpret_cast<const float4 *>(wyb + yo);
+            const float wy4 = *reinterpret_cast<const float *>(wyb + yo + 16);
+            CB2_EDGE_FMA();
         }
-        const float4 *src = STAGED ? reinterpret_cast<const float4 *>(s_rows + (int64_t)row * 8)
-                                   : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + row) * 8);
-        const float4 t0 = src[sw], t1 = src[sw ^ 1];
-        const float2 e[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
-        const float wx = s_wx[dxi * 4 + grp];
-        const float4 wya = s_wy[2 * dyi];
-        const float wy4 = s_wy[2 * dyi + 1].x;
-        const float wy[CB2_G] = {wya.x, wya.y, wya.z, wya.w, wy4};
-#pragma unroll
-        for (int j = 0; j < CB2_G; j++) {
-            const float w = __fmul_rn(wy[j], wx);                       // == tab[c][grp + 3 j] bit for bit (geometry.py)
-            const float2 tt = make_float2(w, w);
-#pragma unroll
-            for (int k = 0; k < 4; k++) A[j][k] = ffma2(tt, e[k], A[j][k]);
+    } else {
+#pragma unroll 1
+        for (int q = -1; q < n; q++) {                                   // q = -1: self loop (offset 0,0)
+            int row, dxi, dyi;
+            if (q < 0) { row = p; dxi = r; dyi = r; }
+            else {
+                row = nbr[(int64_t)q * N + p];
+                const uint32_t d = s_sp[off[(int64_t)q * N + p]];
+                dxi = (int)(d & 31u); dyi = (int)(d >> 5);
+            }
+            const int sw = XA_SWZ(row);
+            const float4 *src = reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + row) * 8);
+            const float4 t0 = src[sw], t1 = src[sw ^ 1];
+            const float wx = s_wx[dxi * 4 + grp];
+            const float4 wya = s_wy[2 * dyi];
+            const float wy4 = s_wy[2 * dyi + 1].x;
+            CB2_EDGE_FMA();
         }
     }
+#undef CB2_EDGE_FMA
     // phase 2: weights from the constant bank through uniform 128-bit loads, two FFMA2 per load
 #pragma unroll
     for (int j = 0; j < CB2_G; j++)
@@ -449,8 +469,8 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     float *s_rows = (float *)smem_raw;                                   // [CB2_CAP][8]   one channel half of the 3 runs
     float *s_wx = s_rows + (size_t)CB2_CAP * 8;                          // [2r+1][4]   x factor of the slot weights
     float4 *s_wy = (float4 *)(s_wx + 128);                               // [2r+1][2]   y factor
-    uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [15][CB2_THREADS]
-    uint16_t *s_sp = (uint16_t *)(s_ell + (DAGR_ELL - 1) * CB2_THREADS); // [ncell]  (dx + r) | (dy + r) << 5
+    uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [16][CB2_THREADS]  slot 0 = self loop
+    uint16_t *s_sp = (uint16_t *)(s_ell + DAGR_ELL * CB2_THREADS);       // [ncell]  (dx + r) | (dy + r) << 5
     const int cell = blockIdx.x;
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
@@ -530,8 +550,9 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             for (int q = 0; q < DAGR_ELL - 1; q++) {
                 const int j = jj[q];
                 const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
-                s_ell[q * CB2_THREADS + tix] = ((uint32_t)row << 12) | ((uint32_t)XA_SWZ(j) << 11) | (uint32_t)s_sp[cc[q]];
+                s_ell[(q + 1) * CB2_THREADS + tix] = ((uint32_t)(2 * row + XA_SWZ(j)) << 4) | ((uint32_t)s_sp[cc[q]] << 16);
             }
+            s_ell[tix] = ((uint32_t)(2 * (p + d1) + XA_SWZ(p)) << 4) | ((uint32_t)(g.r | (g.r << 5)) << 16);   // self loop
         }
         float2 o2[8], sk2[MODE_A ? 8 : 1];
 #pragma unroll
@@ -730,7 +751,7 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
     DAGR_CHECK_ARG(g && p_host, "null argument");
     const int cells = g->B * g->ny1 * g->nx1;
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
-    const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)(DAGR_ELL - 1) * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
+    const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)DAGR_ELL * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
     auto kern = k_l1_conv_b2<dagr_l1b_params_t, 2, false>;
     DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -749,7 +770,7 @@ extern "C" int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32
     if (N <= 0) return DAGR_OK;
     const int cells = g->B * g->ny1 * g->nx1;
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
-    const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)(DAGR_ELL - 1) * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
+    const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)DAGR_ELL * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
     auto kern = k_l1_conv_b2<dagr_l1img_params_t, 3, true>;
     DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
