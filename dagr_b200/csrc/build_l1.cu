@@ -128,19 +128,24 @@ __device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, 
         const int l2 = 2 * d;
         const uint32_t fm = (l2 >= 32) ? 0xffffffffu : ((1u << l2) - 1u);
         const int cbase = (l2 - 1) * (l2 - 1);
-        unsigned long long m = 0;
+        // the 8d mask bits live in two 32-bit words (d <= 8): bit i of `lo` = spiral cell cbase + i, of `hi` = cbase + 32 + i;
+        // popping from a register pair costs a third of the 64-bit find-first-set / clear-lowest sequence
+        uint32_t lo = 0, hi = 0;
         if (n < kmax) {
             const uint32_t leg0 = (occc[tx0 + d] >> (ty0 - d + 1)) & fm;                          // x = +d, y = -d+1 .. d
             const uint32_t leg1 = __brev((occr[ty0 + d] >> (tx0 - d)) & fm) >> (32 - l2);         // y = +d, x = d-1 .. -d
             const uint32_t leg2 = __brev((occc[tx0 - d] >> (ty0 - d)) & fm) >> (32 - l2);         // x = -d, y = d-1 .. -d
             const uint32_t leg3 = (occr[ty0 - d] >> (tx0 - d + 1)) & fm;                          // y = -d, x = -d+1 .. d
-            m = (unsigned long long)leg0 | ((unsigned long long)leg1 << l2) | ((unsigned long long)leg2 << (2 * l2)) |
-                ((unsigned long long)leg3 << (3 * l2));
+            const unsigned long long m = (unsigned long long)leg0 | ((unsigned long long)leg1 << l2) |
+                                         ((unsigned long long)leg2 << (2 * l2)) | ((unsigned long long)leg3 << (3 * l2));
+            lo = (uint32_t)m; hi = (uint32_t)(m >> 32);
         }
-        while (m) {
-            const int i = __ffsll((long long)m) - 1; m &= m - 1;
+        while (lo | hi) {
+            int i;
+            if (lo) { i = __ffs((int)lo) - 1; lo &= lo - 1; }
+            else    { i = 32 + __ffs((int)hi) - 1; hi &= hi - 1; }
             visit(tidx0 + s_sp2[cbase + i], cbase + i);
-            if (n >= kmax) m = 0;
+            if (n >= kmax) { lo = 0; hi = 0; }
         }
     }
     n_out = active ? n : 0;
