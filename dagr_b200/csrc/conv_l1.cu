@@ -383,7 +383,11 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
         // and pass counts as much as an FFMA2.
         const char *rb = reinterpret_cast<const char *>(s_rows);
         const char *wxb = reinterpret_cast<const char *>(s_wx) + 4 * grp, *wyb = reinterpret_cast<const char *>(s_wy);
-#pragma unroll 2
+#ifndef CB2_UNROLL
+#define CB2_UNROLL 1                                                    // measured: 1 -> 1.49 ms, 2 -> 1.56, 3 -> 1.58, 4 -> 1.68 (registers, I-cache)
+#endif
+        constexpr int kUnroll = CB2_UNROLL;
+#pragma unroll kUnroll
         for (int q = 0; q <= n; q++) {
             const uint32_t ell = s_ell[q * CB2_THREADS + tix];
             const uint32_t ro = ell & 0xfff0u, xo = (ell >> 12) & 0x1f0u, yo = (ell >> 16) & 0x3e0u;
