@@ -579,26 +579,32 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
                 parity ^= 1;
             }
             if (active) {
-                // root weight on this half of x_i
+                // root weight on this half of x_i.  `half` must be a compile-time constant here as well: with a run-time index
+                // the 64 weight fetches per half become register-indexed LDC through the address-divergence unit
+#define CB2_ROOT(H)                                                                                                  \
+    do {                                                                                                            \
+        const float4 *src = staged ? reinterpret_cast<const float4 *>(s_rows + (int64_t)(p + d1) * 8)               \
+                                   : reinterpret_cast<const float4 *>(xa + ((int64_t)(H) * N + p) * 8);             \
+        const float4 t0 = src[XA_SWZ(p)], t1 = src[XA_SWZ(p) ^ 1];                                                  \
+        const float v[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};                                        \
+        _Pragma("unroll") for (int k = 0; k < 8; k++)                                                               \
+            _Pragma("unroll") for (int c4 = 0; c4 < 4; c4++) {                                                      \
+                const float4 w4 = *reinterpret_cast<const float4 *>(&P.root[8 * (H) + k][4 * c4]);                  \
+                o2[2 * c4] = ffma2(make_float2(v[k], v[k]), make_float2(w4.x, w4.y), o2[2 * c4]);                   \
+                o2[2 * c4 + 1] = ffma2(make_float2(v[k], v[k]), make_float2(w4.z, w4.w), o2[2 * c4 + 1]);           \
+                if constexpr (MODE_A) {                  /* the layer's skip branch Linear(x0) (conv.py:41-52) */    \
+                    const float4 k4 = *reinterpret_cast<const float4 *>(&P.skip[8 * (H) + k][4 * c4]);              \
+                    sk2[2 * c4] = ffma2(make_float2(v[k], v[k]), make_float2(k4.x, k4.y), sk2[2 * c4]);             \
+                    sk2[2 * c4 + 1] = ffma2(make_float2(v[k], v[k]), make_float2(k4.z, k4.w), sk2[2 * c4 + 1]);     \
+                }                                                                                                   \
+            }                                                                                                       \
+    } while (0)
                 if (!sparse || wid_ == 0) {
-                    const float4 *src = staged ? reinterpret_cast<const float4 *>(s_rows + (int64_t)(p + d1) * 8)
-                                               : reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + p) * 8);
-                    const float4 t0 = src[XA_SWZ(p)], t1 = src[XA_SWZ(p) ^ 1];
-                    const float v[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) {
-                            const float4 w4 = *reinterpret_cast<const float4 *>(&P.root[8 * half + k][4 * c4]);
-                            o2[2 * c4] = ffma2(make_float2(v[k], v[k]), make_float2(w4.x, w4.y), o2[2 * c4]);
-                            o2[2 * c4 + 1] = ffma2(make_float2(v[k], v[k]), make_float2(w4.z, w4.w), o2[2 * c4 + 1]);
-                            if constexpr (MODE_A) {                      // the layer's skip branch Linear(x0) (conv.py:41-52)
-                                const float4 k4 = *reinterpret_cast<const float4 *>(&P.skip[8 * half + k][4 * c4]);
-                                sk2[2 * c4] = ffma2(make_float2(v[k], v[k]), make_float2(k4.x, k4.y), sk2[2 * c4]);
-                                sk2[2 * c4 + 1] = ffma2(make_float2(v[k], v[k]), make_float2(k4.z, k4.w), sk2[2 * c4 + 1]);
-                            }
-                        }
+                    if (half == 0)      CB2_ROOT(0);
+                    else if (half == 1) CB2_ROOT(1);
+                    else if constexpr (NCH > 2) CB2_ROOT(2);
                 }
+#undef CB2_ROOT
 #define CB2_PASS(H, G)                                                                                               \
     do {                                                                                                            \
         if (staged) cb2_pass<true, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2); \
