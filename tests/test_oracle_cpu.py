@@ -314,3 +314,47 @@ def test_ingest_window_oracle_identities():
     assert np.all(np.abs(den[:, 2] - t_rel) <= 1) and den[-1, 2] in (T, T - 1)       # fp32 round trip may lose 1 us
     den0, pol0 = R.preprocess_window({k: v[:0] for k, v in ev.items()}, W, H, T)
     assert den0.shape == (0, 3) and pol0.shape == (0,)
+
+
+def test_detection_records_match_the_reference_golden(tmp_path):
+    """dagr_b200.utils.buffers (host-side detection records) against arrays produced by the reference's
+    own src/dagr/utils/buffers.py (tests/golden/make_records_golden.py)."""
+    import numpy as np
+    from pathlib import Path
+    from dagr.utils import buffers as B                      # the drop-in import path of the reference
+    g = np.load(Path(__file__).parent / "golden" / "records_golden.npz")
+    dets = [dict(boxes=torch.from_numpy(g[f"det{i}_boxes"]), scores=torch.from_numpy(g[f"det{i}_scores"]),
+                 labels=torch.from_numpy(g[f"det{i}_labels"])) for i in range(4)]
+    gts = [dict(boxes=torch.from_numpy(g[f"gt{i}_boxes"]), labels=torch.from_numpy(g[f"gt{i}_labels"])) for i in range(4)]
+    seqs, ts = ["zurich_a", "zurich_a", "interlaken_b", "zurich_a"], [1000, 51000, 7, 101000]
+    buf = B.DetectionBuffer(height=430, width=640, classes=["car", "pedestrian"])
+    buf.update([{k: v.clone() for k, v in d.items()} for d in dets], [{k: v.clone() for k, v in d.items()} for d in gts], "dsec")
+    cd, cg = buf.compile(seqs, ts)
+    for s in ("zurich_a", "interlaken_b"):
+        assert cd[s].dtype == g[f"compiled_det_{s}"].dtype and np.array_equal(cd[s], g[f"compiled_det_{s}"])
+        assert cg[s].dtype == g[f"compiled_gt_{s}"].dtype and np.array_equal(cg[s], g[f"compiled_gt_{s}"])
+    flt = B.filter_bboxes([{k: v.clone() for k, v in d.items()} for d in dets], 430, 640)
+    for i, d in enumerate(flt):
+        for k, v in d.items():
+            assert np.array_equal(v.numpy(), g[f"filt{i}_{k}"]), (i, k)
+    db = B.DictBuffer()
+    for d in ({"a": 1.0, "b": 4.0}, {"a": 3.0, "b": 0.0}, {"a": 8.0, "b": 2.0}):
+        db.update(d)
+    assert np.allclose([db.compute()["a"], db.compute()["b"]], g["dictbuffer"], rtol=0, atol=0)
+    # run_test_interframe's to_npy / save_detections and the batched device form give the same records
+    recs = [B.to_npy(dict(boxes=d["boxes"].numpy(), labels=d["labels"].numpy(), scores=d["scores"].numpy(), t=t)) for d, t in zip(dets, ts)]
+    for r, d, t in zip(recs, dets, ts):
+        ref = B.bbox_t_to_ndarray(d, t)
+        assert r.dtype == ref.dtype and np.array_equal(r, ref)
+    saved = B.save_detections(tmp_path, [dict(boxes=d["boxes"].numpy(), labels=d["labels"].numpy(), scores=d["scores"].numpy(), t=t, sequence=s)
+                                         for d, t, s in zip(dets, ts, seqs)])
+    assert np.array_equal(np.load(tmp_path / "detections_zurich_a.npy"), saved["zurich_a"])
+    assert np.all(np.diff(saved["zurich_a"]["t"].astype(np.int64)) >= 0) and len(saved["zurich_a"]) == 8 and len(saved["interlaken_b"]) == 7
+    A = 8
+    det = torch.zeros(4, A, 6)
+    ndet = torch.tensor([len(d["boxes"]) for d in dets], dtype=torch.int32)
+    for b, d in enumerate(dets):
+        n = len(d["boxes"])
+        det[b, :n, :4], det[b, :n, 4], det[b, :n, 5] = d["boxes"], d["scores"], d["labels"].float()
+    for r, ref in zip(B.records_from_device(det, ndet, ts), recs):
+        assert r.dtype == ref.dtype and np.array_equal(r, ref)
