@@ -358,3 +358,38 @@ def test_detection_records_match_the_reference_golden(tmp_path):
         det[b, :n, :4], det[b, :n, 4], det[b, :n, 5] = d["boxes"], d["scores"], d["labels"].float()
     for r, ref in zip(B.records_from_device(det, ndet, ts), recs):
         assert r.dtype == ref.dtype and np.array_equal(r, ref)
+
+
+def test_reference_style_eval_loop_runs_with_a_stub_model():
+    """dagr.utils.testing.run_test_with_visualization (src/dagr/utils/testing.py:16-60): loop semantics with a stub
+    model and loader (no GPU needed: the loop is harness code around model(data))."""
+    from dagr.utils.testing import run_test_with_visualization
+    from dagr_b200.data import synth_batch
+
+    class DS:
+        height, width, classes = 48, 64, ["car", "pedestrian"]
+
+    class Loader(list):
+        dataset = DS()
+
+    class Model:
+        def eval(self):
+            return self
+
+        def __call__(self, data):
+            assert data.pos.dtype == torch.float32 and data.pos.shape[1] == 3          # format_data was applied
+            B = int(data.num_graphs)
+            det = [dict(boxes=torch.tensor([[1.0, 2.0, 11.0, 22.0]]) + b, scores=torch.tensor([0.5]), labels=torch.tensor([b % 2])) for b in range(B)]
+            tgt = [dict(boxes=torch.tensor([[0.0, 0.0, 5.0, 5.0]]), labels=torch.tensor([0])) for _ in range(B)]
+            return det, tgt
+
+    batches = []
+    for k in range(3):
+        d = synth_batch(2, 50, 64, 48, seed=k)
+        d.sequence, d.t1 = [f"seq{k}", f"seq{k}"], [100 * k, 100 * k + 1]
+        batches.append(d)
+    if torch.cuda.is_available():
+        pytest.skip("stub loop test is for the CPU suite")
+    res, comp = run_test_with_visualization(Loader(batches), Model(), "dsec", compile_detections=True, no_eval=True)
+    assert res is None and len(comp) == 6 and comp[3]["sequence"] == "seq1" and comp[3]["t"] == 101
+    assert comp[0]["boxes"].shape == (1, 4) and comp[1]["labels"].tolist() == [1]
