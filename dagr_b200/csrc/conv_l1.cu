@@ -379,8 +379,8 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
     if constexpr (STAGED) {
         // the ELL word carries ready-made BYTE offsets: bits 4..15 = 16 * (2 * row + row swizzle) (first 16-byte chunk of
         // the staged half-row; the other chunk is that offset ^ 16), bits 16..20 = dx + r, bits 21..25 = dy + r.  Slot 0 is
-        // the self loop.  The integer pipe issues at half rate like the FMA pipe, so every shift/mask/add saved per edge
-        // and pass counts as much as an FFMA2.
+        // the self loop.  Every instruction costs an issue slot (one per cycle and SMSP) and the loop is issue bound, so
+        // the 8 shifts/masks/adds this saves per edge and pass were worth 9 % of the kernel (profiles/r01_ubench_pipes.txt).
         const char *rb = reinterpret_cast<const char *>(s_rows);
         const char *wxb = reinterpret_cast<const char *>(s_wx) + 4 * grp, *wyb = reinterpret_cast<const char *>(s_wy);
 #ifndef CB2_UNROLL

@@ -1,5 +1,5 @@
-// pipes.cu -- micro-benchmarks of the per-SM issue rates this round's kernel decisions leaned on (NOT part of the library;
-// NOT yet run: written at the end of round 1 when the GPU budget was spent -- run it first thing in round 2):
+// pipes.cu -- micro-benchmarks of the per-SM issue rates this round's kernel decisions leaned on (not part of the library;
+// B200 results: profiles/r01_ubench_pipes.txt):
 //   * FFMA vs packed FFMA2 (fma.rn.f32x2) issue rate per SMSP
 //   * IADD3/LOP3 (integer pipe) issue rate per SMSP
 //   * LDS.32 / LDS.128 with a warp-uniform address (broadcast) and with conflict-free per-lane addresses
