@@ -1,29 +1,19 @@
-"""ModelEMA (reference: src/dagr/model/networks/ema.py:6-51), eval-side surface only."""
-import math
-from copy import deepcopy
+"""Evaluation-side stand-in for the reference's ModelEMA wrapper (src/dagr/model/networks/ema.py:17-33).
 
-import torch
+scripts/run_test.py:56-62 builds `ModelEMA(model)`, loads `checkpoint['ema']` into `.ema` and evaluates `.ema`;
+that is all this class supports: a frozen eval-mode copy of the detector.  The training-time weight averaging of
+the reference is out of scope.
+"""
+import copy
 
 
 class ModelEMA:
-    def __init__(self, model, decay=0.9999, updates=0):
-        self.ema = deepcopy(model).eval()
-        try:
-            self.ema.backbone.net.remove_hooks()
-            self.ema.backbone.net.register_hooks()
-        except Exception:
-            pass
-        self.updates = updates
-        self.decay = lambda x: decay * (1 - math.exp(-x / 2000))
-        for p in self.ema.parameters():
-            p.requires_grad_(False)
-
-    def update(self, model):
-        with torch.no_grad():
-            self.updates += 1
-            d = self.decay(self.updates)
-            msd = model.state_dict()
-            for k, v in self.ema.state_dict().items():
-                if v.dtype.is_floating_point:
-                    v *= d
-                    v += (1.0 - d) * msd[k].detach()
+    def __init__(self, model, **_ignored_training_options):
+        frozen = copy.deepcopy(model)
+        frozen.eval()
+        frozen.requires_grad_(False)
+        net = getattr(getattr(frozen, "backbone", None), "net", None)
+        if net is not None and hasattr(net, "register_hooks"):       # image trunk: hooks do not survive deepcopy
+            net.remove_hooks()
+            net.register_hooks()
+        self.ema = frozen

@@ -93,8 +93,9 @@ class RefModel:
 
     # --------------------------------------------------------------------------------------------
     def forward(self, x, pos, batch, batch_size, image_feats=None, image_outs=None, filtering=True,
-                conf_thre=0.001, nms_thre=0.65):
-        """x fp32[N,1], pos fp32[N,3] normalised, batch int64[N]  (all CPU)."""
+                conf_thre=0.001, nms_thre=0.65, pos_hints=None, mirror_t_quirk=True):
+        """x fp32[N,1], pos fp32[N,3] normalised, batch int64[N]  (all CPU).
+        pos_hints: optional list of 4 fp32 [n_level,2] tensors, see ref_ops.pooling(pos_hint=...)."""
         args, W, H = self.args, self.W, self.H
         out = {}
         T = int(getattr(args, "time_window_us", 1000000))
@@ -126,7 +127,8 @@ class RefModel:
                 pooled = None
             else:
                 pooled = R.pooling(g.x, g.pos, g.batch, g.edge_index, self.poolings[i], W, H, batch_size, cart_max[i],
-                                   aggr=aggrs[i], keep_temporal_ordering=getattr(args, "keep_temporal_ordering", False))
+                                   aggr=aggrs[i], keep_temporal_ordering=getattr(args, "keep_temporal_ordering", False),
+                                   pos_hint=None if pos_hints is None else pos_hints[i], mirror_t_quirk=mirror_t_quirk)
             if pooled is None:
                 levels.append(None)
                 pg = g

@@ -313,12 +313,16 @@ def round_to_pixel(pos: torch.Tensor, wh_inv: torch.Tensor):
 
 
 def pooling(x, pos, batch, edge_index, voxel_size3, width, height, batch_size, cart_max, aggr="max",
-            keep_temporal_ordering=False, exact_mean=True):
+            keep_temporal_ordering=False, exact_mean=True, pos_hint=None, mirror_t_quirk=True):
     """Pooling.forward (pooling.py:51-97).  Returns dict(x,pos,batch,edge_index,edge_attr,cluster,ambiguous).
 
     `exact_mean`: the reference's pooled position is an fp32 atomic mean (run-to-run unstable);
     the oracle computes it in float64 and flags clusters whose pixel rounding is within float
     noise of a boundary (`ambiguous`), see SURVEY H3(b).
+    `pos_hint` (fp32 [n,2], optional): rounded positions to adopt for the clusters the oracle itself flags as
+    ambiguous, so that a comparison can continue below such a voxel instead of stopping (the reference is not
+    run-to-run stable there).  `mirror_t_quirk=False` keeps an event with normalised t == 1.0 (dsec_data.py:145)
+    in temporal cell 0 instead of letting it alias into the next sample's voxel.
     """
     if x.shape[0] == 0:
         return None
@@ -327,6 +331,8 @@ def pooling(x, pos, batch, edge_index, voxel_size3, width, height, batch_size, c
     end = torch.Tensor([0.9999999, 0.9999999, 0.9999999, batch_size - 1])     # :31
     wh_inv = 1 / torch.Tensor([[width, height]])                               # :32
     pos4 = torch.cat([pos, batch.float().view(-1, 1)], dim=-1)                 # :55
+    if not mirror_t_quirk:
+        pos4[:, 2] = pos4[:, 2].clamp(max=0.9999999)
     cluster = grid_cluster(pos4, voxel_size, start, end)                       # :56
     uniq, cl, perm, _ = consecutive_cluster(cluster)                            # :57
     n = uniq.shape[0]
@@ -354,6 +360,8 @@ def pooling(x, pos, batch, edge_index, voxel_size3, width, height, batch_size, c
     ambiguous = ((frac < 2e-3) | (frac > 1 - 2e-3)).any(dim=1)
     npos = npos.clone()
     npos[:, :2] = round_to_pixel(npos[:, :2], wh_inv)                           # :86
+    if pos_hint is not None and bool(ambiguous.any()) and pos_hint.shape[0] == n:
+        npos[ambiguous, :2] = pos_hint[ambiguous].to(npos.dtype)
     edge_attr = cartesian(npos, ei, cart_max) if ei.shape[1] > 0 else torch.zeros((0, npos.shape[1]))
     return dict(x=nx, pos=npos, batch=nbatch, edge_index=ei, edge_attr=edge_attr, cluster=cl,
                 unique_clusters=uniq, ambiguous=ambiguous)

@@ -21,10 +21,29 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float(((a - b).abs() / (b.abs() + s)).max())
 
 
+def plain_rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max |a-b|/|b| over the elements with |b| > 1e-3 * mean|b| (plain relative error, no softening term)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    if b.numel() == 0:
+        return 0.0
+    m = b.abs() > 1e-3 * b.abs().mean().clamp(min=1e-12)
+    if not bool(m.any()):
+        return 0.0
+    return float(((a - b).abs()[m] / b.abs()[m]).max())
+
+
+# every assert_close call leaves (softened, plain) max relative errors here; tests/conftest.py dumps the table to
+# gpurun_out/parity_errors.json at the end of a GPU session (committed copy: profiles/r02_parity_errors.json)
+ERROR_LOG = {}
+
+
 def assert_close(a, b, tol=RTOL, what=""):
     assert a.shape == b.shape, (what, a.shape, b.shape)
     e = rel_err(a, b)
-    assert e <= tol, f"{what}: relative error {e:.3e} > {tol:.1e}"
+    pe = plain_rel_err(a, b)
+    prev = ERROR_LOG.get(what, (0.0, 0.0, 0))
+    ERROR_LOG[what] = (max(prev[0], e), max(prev[1], pe), prev[2] + 1)
+    assert e <= tol, f"{what}: relative error {e:.3e} > {tol:.1e} (plain relative, |ref| > 1e-3 mean: {pe:.3e})"
 
 
 def randomize_bn(model, seed=1):

@@ -214,53 +214,67 @@ FWD_CASES = [
 ]
 
 
-@pytest.mark.parametrize("W,H,B,n,kind,size,dataset", FWD_CASES)
-def test_forward_parity_vs_oracle(W, H, B, n, kind, size, dataset):
+def _pos_hints(L):
+    """the product's rounded pooled positions per level (normalised), handed to the oracle for the voxels the oracle
+    itself flags as ambiguous (mean within float noise of a pixel boundary; the reference's fp32 atomic mean is not
+    run-to-run stable there) so that the comparison continues below such a voxel."""
+    from dagr_b200 import export
+    geom = L["geom"]
+    return [export.grid_nodes(L["grids"][lv], geom.levels[lv], geom)["pos"].cpu() for lv in range(4)]
+
+
+def _check_forward(model, args, data, B, H, W, image=False, mirror_t_quirk=True, check_public=True):
+    """full comparison of one forward with the oracle: edges bit-exact, per-event activations, every pooled level
+    (node sets, batch, rounded positions, coarse edges bit-exact; features 1e-4), out3/out4, dense head maps, decoded
+    outputs and the detections of the public forward."""
     from dagr_b200 import export
     from oracle.ref_model import RefModel
-    model, args = make_model(size, H, W, dataset=dataset)
-    model.cuda()
-    raw, data = make_inputs(B, n, W, H, seed=31, kind=kind, ragged=True)
-    dec, batch_i, pos_i = _run_graph(model, data, B)
     eng = model.engine
+    eng.keep_node_features = True
+    d = data.clone().cuda()
+    if image:
+        dec = model.forward_decoded(d)
+    else:
+        batch_i, pos_i, feat, _, _ = model._prepare_events(d)
+        dec = eng.forward_events(batch_i, pos_i, feat, B, W, H)
+    torch.cuda.synchronize()
+    dec = dec.clone()
     L = eng.last
     N = L["N"]
     ref = RefModel({k: v.cpu() for k, v in model.state_dict().items()}, args, H, W)
-    o = ref.forward(data.x, data.pos, data.batch, B)
+    kw = {}
+    if image:
+        kw = dict(image_feats=[f.cpu() for f in model.last_image_feats],
+                  image_outs={k: [t.cpu() for t in v] for k, v in model.last_image_outs.items()})
+    o = ref.forward(data.x, data.pos, data.batch, B, pos_hints=_pos_hints(L), mirror_t_quirk=mirror_t_quirk, **kw)
 
     # event level: edges bit-exact, features within tolerance (arrival order)
-    assert torch.equal(eng.export_edges().cpu(), o["edge_index"])
+    mine = eng.export_edges().cpu()
+    assert mine.shape == o["edge_index"].shape, (mine.shape, o["edge_index"].shape)
+    assert torch.equal(mine, o["edge_index"])
     perm = L["ws"]["perm"]
-    xa = export.unsort_rows(eng.xa_rows(), perm, N).cpu()
-    x1 = export.unsort_rows(L["x1"], perm, N).cpu()
-    assert_close(xa, o["x1a"], what="conv_block1.conv_block1 output")
-    assert_close(x1, o["x1"], what="conv_block1 output")
+    assert_close(export.unsort_rows(eng.xa_rows(), perm, N).cpu(), o["x1a"], what="conv_block1.conv_block1 output")
+    assert_close(export.unsort_rows(L["x1"], perm, N).cpu(), o["x1"], what="conv_block1 output")
 
     # pooled levels: node sets / positions / coarse edges bit-exact, features within tolerance
     geom = L["geom"]
-    feats = [L["grids"][0].x, L["grids"][1].x, L["grids"][2].x, L["grids"][3].x]
     for lv in range(4):
         gs, level, pl = L["grids"][lv], geom.levels[lv], o["levels"][lv]
         nodes = export.grid_nodes(gs, level, geom)
         assert len(nodes["cell"]) == pl["x"].shape[0], f"level {lv}: node count"
         assert torch.equal(nodes["batch"].cpu(), pl["batch"]), f"level {lv}: batch"
-        amb = pl["ambiguous"]
-        same = nodes["pos"].cpu() == pl["pos"][:, :2]
-        assert bool(same[~amb].all()), f"level {lv}: rounded positions"
-        e = export.grid_edges(gs, level).cpu()
-        assert torch.equal(e, pl["edge_index"]), f"level {lv}: coarse edge_index"
+        # ambiguous voxels adopted the product's position in the oracle (pos_hints): everything else is bit-exact
+        assert torch.equal(nodes["pos"].cpu(), pl["pos"][:, :2]), f"level {lv}: rounded positions"
+        assert torch.equal(export.grid_edges(gs, level).cpu(), pl["edge_index"]), f"level {lv}: coarse edge_index"
         assert_close(nodes["x"].cpu(), pl["x"], what=f"level {lv} pooled features")
-        if not bool(same.all()):
-            # the oracle itself flags these voxels: their mean position is within float noise of a pixel boundary
-            # (the reference's atomic fp32 mean is not run-to-run stable there)
-            pytest.skip("pooled position differs only at oracle-flagged ambiguous voxels: deeper levels not comparable")
     assert_close(L["inter"]["o4"][L["grids"][2].cnt[:L["grids"][2].cells] > 0].cpu(), o["out3"], what="out3")
     assert_close(L["inter"]["o5"][L["grids"][3].cnt[:L["grids"][3].cells] > 0].cpu(), o["out4"], what="out4")
-    for k, d in enumerate(L["dense"]):
+    for k, dd in enumerate(L["dense"]):
         for name in ("cls", "reg", "obj"):
-            assert_close(d[name].cpu(), o["dense"][k][name], what=f"dense {name}{k + 1}")
+            assert_close(dd[name].cpu(), o["dense"][k][name], what=f"dense {name}{k + 1}")
     assert_close(dec.cpu(), o["decoded"], what="decoded outputs")
-
+    if not check_public:
+        return o
     # detections through the public forward
     dets = model(data.clone().cuda())[0]
     assert len(dets) == B
@@ -271,6 +285,64 @@ def test_forward_parity_vs_oracle(W, H, B, n, kind, size, dataset):
             assert torch.equal(dets[b]["labels"].cpu(), rb["labels"])
             assert_close(dets[b]["boxes"].cpu(), rb["boxes"], what="boxes")
             assert_close(dets[b]["scores"].cpu(), rb["scores"], what="scores")
+    return o
+
+
+@pytest.mark.parametrize("W,H,B,n,kind,size,dataset", FWD_CASES)
+def test_forward_parity_vs_oracle(W, H, B, n, kind, size, dataset):
+    model, args = make_model(size, H, W, dataset=dataset)
+    model.cuda()
+    raw, data = make_inputs(B, n, W, H, seed=31, kind=kind, ragged=True)
+    _check_forward(model, args, data, B, H, W)
+
+
+# the BENCHMARKED regime (BASELINE.json configs[1]: dagr-s, 640x480, 300k events per sample in a 50 ms window): mean
+# degree ~15.4 with the K cap saturated almost everywhere, > 160 events per pool1 voxel (multi-chunk loops of the
+# per-voxel kernels), multi-record pixels; the clustered stream adds voxels beyond the staging capacities
+# (BL_CAP / CB2_CAP -> global-memory fallbacks) and low-degree noise events.
+FULL_DENSITY_CASES = [
+    (1, "uniform", 2042),                 # one sample of the bench batch (bench.py seed 42 + 1000 * 2)
+    (1, "clustered", 2042),
+    (2, "uniform", 2052),
+]
+
+
+@pytest.mark.parametrize("B,kind,seed", FULL_DENSITY_CASES)
+def test_full_density_forward_parity_vs_oracle(B, kind, seed):
+    W, H, n = 640, 480, 300000
+    model, args = make_model("s", H, W, batch_size=B)
+    model.cuda()
+    raw, data = make_inputs(B, n, W, H, seed=seed, kind=kind)
+    _check_forward(model, args, data, B, H, W)
+    N = model.engine.last["N"]
+    deg = model.engine.last["ws"]["nbr"][15 * N:16 * N].float()
+    if kind == "uniform":
+        assert float(deg.mean()) > 13.0                       # the K cap (15 neighbours + self loop) is hit almost everywhere
+
+
+def test_last_event_at_t_equals_T_quirk_h3a():
+    """Quirk Q1 / H3a (dsec_data.py:145, pooling.py:31,56): real DSEC windows end with an event at normalised t == 1.0,
+    which torch_cluster.grid_cluster puts into temporal cell 1 of a one-cell axis, so in the reference it aliases into the
+    NEXT sample's voxel (or a phantom voxel behind the last sample).  The graph build does not care (edges stay
+    bit-exact).  The kernels key voxels by (batch, y, x) only, i.e. they keep the event in its own sample's voxel: the
+    forward equals the oracle with the quirk switched off, and the oracle with the quirk on differs (documented gap)."""
+    from dagr_b200.data import EventBatch
+    from oracle.ref_model import RefModel
+    W, H, B, T = 320, 215, 2, 1_000_000
+    model, args = make_model("s", H, W, batch_size=B)
+    model.cuda()
+    raw, data = make_inputs(B, 9000, W, H, seed=77, kind="uniform")
+    pos = data.pos.clone()
+    for b in range(B):
+        last = int(torch.nonzero(data.batch == b).flatten()[-1])
+        pos[last, 2] = 1.0                                        # t == T exactly (dsec_data.py:145)
+    d = EventBatch(x=data.x, pos=pos, batch=data.batch, width=data.width, height=data.height, time_window=data.time_window, num_graphs=B)
+    o = _check_forward(model, args, d, B, H, W, mirror_t_quirk=False)
+    ref = RefModel({k: v.cpu() for k, v in model.state_dict().items()}, args, H, W)
+    q = ref.forward(d.x, d.pos, d.batch, B, mirror_t_quirk=True)
+    assert torch.equal(q["edge_index"], o["edge_index"])
+    # with the quirk the last event of the last sample lands in a phantom voxel behind the batch
+    assert q["levels"][0]["x"].shape[0] == o["levels"][0]["x"].shape[0] + 1
 
 
 @pytest.mark.parametrize("W,H,B,n,size", [(240, 180, 2, 5000, "n"), (320, 215, 1, 9000, "s")])
