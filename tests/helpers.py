@@ -2,6 +2,8 @@
 import argparse
 import copy
 
+import numpy as np
+
 import torch
 
 from dagr_b200.data import EventBatch, format_data, synth_batch
@@ -77,3 +79,80 @@ def make_inputs(B, n_events, width, height, seed=42, kind="uniform", ragged=Fals
     raw = synth_batch(B, n_events, width, height, seed=seed, kind=kind, ragged=ragged, window_us=window_us)
     data = format_data(raw.clone())
     return raw, data
+
+
+def golden_weights(model: torch.nn.Module, seed: int):
+    """deterministic, non-trivial values for EVERY floating tensor of a state_dict (keys in sorted order, one CPU
+    generator): both the reference model and this repo's model are filled by the same rule, so fixtures only store
+    inputs and outputs.  BN statistics / affine are kept away from the identity."""
+    sd = model.state_dict()
+    g = torch.Generator().manual_seed(int(seed))
+    keys = sorted(sd.keys())
+    new = {}
+    for k in keys:
+        t = sd[k]
+        if not t.dtype.is_floating_point:
+            new[k] = t.clone()
+            continue
+        shape = tuple(t.shape)
+        prefix = k.rsplit(".", 1)[0]
+        is_bn = (prefix + ".running_mean") in sd
+        if k.endswith("running_var"):
+            v = 0.5 + torch.rand(shape, generator=g)
+        elif k.endswith("running_mean"):
+            v = 0.1 * torch.randn(shape, generator=g)
+        elif is_bn and k.endswith("weight"):
+            v = 0.5 + torch.rand(shape, generator=g)
+        elif len(shape) <= 1:
+            v = 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan = shape[1] if len(shape) == 2 else 2 * shape[1] if len(shape) == 3 else int(np.prod(shape[1:]))
+            v = torch.randn(shape, generator=g) / float(np.sqrt(max(fan, 1)))
+            if "_pred" in k:                                      # keep exp(wh) of the decode finite
+                v = v * 0.1
+        new[k] = v.to(t.dtype)
+    model.load_state_dict(new, strict=True)
+    return float(sum(v.double().abs().sum() for v in new.values() if v.dtype.is_floating_point))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fixtures produced by the REFERENCE's own model code (tests/golden/make_reference_forward_golden.py)
+# ------------------------------------------------------------------------------------------------------------------
+REFERENCE_FIXTURES = ("events_s_320x215", "events_n_ncaltech_240x180", "image_n_240x180")
+
+
+def load_reference_fixture(name):
+    """-> (model on CPU with the fixture's weights, args, data (EventBatch, formatted), expected dict shaped like
+    oracle.ref_model.RefModel.forward's output, meta)."""
+    from pathlib import Path
+    from dagr_b200.model.dagr import DAGR
+    f = np.load(Path(__file__).resolve().parent / "golden" / f"reference_forward_{name}.npz")
+    W, H, B, seed, use_image = (int(v) for v in f["meta"])
+    args = default_args(str(f["size"]), dataset=str(f["dataset"]), batch_size=B, use_image=bool(use_image), img_net="resnet18")
+    torch.manual_seed(0)
+    model = DAGR(args, height=H, width=W).eval()
+    checksum = golden_weights(model, seed)
+    # same key set, same shapes, same deterministic rule as the reference's module tree -> same numbers
+    assert abs(checksum - float(f["weight_checksum"])) <= 1e-9 * checksum, "state_dict layout differs from the reference's"
+    t = lambda k: torch.from_numpy(f[k])
+    data = EventBatch(x=t("x"), pos=t("pos"), batch=t("batch").long(), width=torch.full((B,), W), height=torch.full((B,), H),
+                      time_window=torch.full((B,), 1_000_000), num_graphs=B)
+    if use_image:
+        data.image = t("image_u8").float() / 255.0
+    nscale = args.num_scales
+    exp = dict(edge_index=t("edge_index").long(), x1a=t("x1a"), x1=t("x1"), out3=t("out3"), out4=t("out4"), decoded=t("decoded"),
+               levels=[dict(x=t(f"level{i}_x"), pos=t(f"level{i}_pos"), batch=t(f"level{i}_batch").long(),
+                            edge_index=t(f"level{i}_edge_index").long(), ambiguous=t(f"level{i}_ambiguous")) for i in range(4)],
+               dense=[{nm: t(f"dense_{nm}{k + 1}") for nm in ("cls", "reg", "obj")} for k in range(nscale)],
+               detections=[dict(boxes=t(f"det{b}_boxes"), scores=t(f"det{b}_scores"), labels=t(f"det{b}_labels").long()) for b in range(B)])
+    return model, args, data, exp, dict(W=W, H=H, B=B, use_image=bool(use_image), num_scales=nscale)
+
+
+def image_branch_cpu(model, data):
+    """the dense image trunk + CNN head on the CPU in fp32 (library code on both sides): the tensors the graph path consumes."""
+    with torch.no_grad():
+        feats, outs = model.backbone.net(data.image.float())
+        sizes = model.backbone.get_output_sizes()[-model.head.num_scales:]
+        cnn_in = [torch.nn.functional.interpolate(o, size=tuple(sz)) for o, sz in zip(outs[-model.head.num_scales:], sizes)]
+        image_outs = model.head.cnn_head(cnn_in)
+    return [f.float().contiguous() for f in feats], {k: [t.float().contiguous() for t in v] for k, v in image_outs.items()}

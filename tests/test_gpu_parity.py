@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import RTOL, assert_close, make_inputs, make_model, rel_err
+from tests.helpers import REFERENCE_FIXTURES, RTOL, assert_close, make_inputs, make_model, rel_err
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
@@ -223,12 +223,7 @@ def _pos_hints(L):
     return [export.grid_nodes(L["grids"][lv], geom.levels[lv], geom)["pos"].cpu() for lv in range(4)]
 
 
-def _check_forward(model, args, data, B, H, W, image=False, mirror_t_quirk=True, check_public=True):
-    """full comparison of one forward with the oracle: edges bit-exact, per-event activations, every pooled level
-    (node sets, batch, rounded positions, coarse edges bit-exact; features 1e-4), out3/out4, dense head maps, decoded
-    outputs and the detections of the public forward."""
-    from dagr_b200 import export
-    from oracle.ref_model import RefModel
+def _run_product(model, data, B, H, W, image_feats=None, image_outs=None, image=False):
     eng = model.engine
     eng.keep_node_features = True
     d = data.clone().cuda()
@@ -236,56 +231,94 @@ def _check_forward(model, args, data, B, H, W, image=False, mirror_t_quirk=True,
         dec = model.forward_decoded(d)
     else:
         batch_i, pos_i, feat, _, _ = model._prepare_events(d)
-        dec = eng.forward_events(batch_i, pos_i, feat, B, W, H)
+        dec = eng.forward_events(batch_i, pos_i, feat, B, W, H, image_feats=image_feats, image_outs=image_outs)
     torch.cuda.synchronize()
-    dec = dec.clone()
+    return dec.clone()
+
+
+def _compare_with(model, dec, o, hinted=True, dense=True):
+    """product state of the last forward vs an expected dict shaped like RefModel.forward's output (the oracle's, or a
+    fixture produced by the reference's own code): edges bit-exact, per-event activations, every pooled level (node sets,
+    batch, rounded positions, coarse edges bit-exact; features 1e-4), out3/out4, dense head maps, decoded outputs."""
+    from dagr_b200 import export
+    eng = model.engine
     L = eng.last
     N = L["N"]
-    ref = RefModel({k: v.cpu() for k, v in model.state_dict().items()}, args, H, W)
-    kw = {}
-    if image:
-        kw = dict(image_feats=[f.cpu() for f in model.last_image_feats],
-                  image_outs={k: [t.cpu() for t in v] for k, v in model.last_image_outs.items()})
-    o = ref.forward(data.x, data.pos, data.batch, B, pos_hints=_pos_hints(L), mirror_t_quirk=mirror_t_quirk, **kw)
-
-    # event level: edges bit-exact, features within tolerance (arrival order)
     mine = eng.export_edges().cpu()
     assert mine.shape == o["edge_index"].shape, (mine.shape, o["edge_index"].shape)
     assert torch.equal(mine, o["edge_index"])
     perm = L["ws"]["perm"]
     assert_close(export.unsort_rows(eng.xa_rows(), perm, N).cpu(), o["x1a"], what="conv_block1.conv_block1 output")
     assert_close(export.unsort_rows(L["x1"], perm, N).cpu(), o["x1"], what="conv_block1 output")
-
-    # pooled levels: node sets / positions / coarse edges bit-exact, features within tolerance
     geom = L["geom"]
     for lv in range(4):
         gs, level, pl = L["grids"][lv], geom.levels[lv], o["levels"][lv]
         nodes = export.grid_nodes(gs, level, geom)
         assert len(nodes["cell"]) == pl["x"].shape[0], f"level {lv}: node count"
         assert torch.equal(nodes["batch"].cpu(), pl["batch"]), f"level {lv}: batch"
-        # ambiguous voxels adopted the product's position in the oracle (pos_hints): everything else is bit-exact
-        assert torch.equal(nodes["pos"].cpu(), pl["pos"][:, :2]), f"level {lv}: rounded positions"
+        same = (nodes["pos"].cpu() == pl["pos"][:, :2]).all(1)
+        if hinted:
+            # ambiguous voxels adopted the product's position in the oracle (pos_hints): everything is bit-exact
+            assert bool(same.all()), f"level {lv}: rounded positions"
+        else:
+            assert bool(same[~pl["ambiguous"]].all()), f"level {lv}: rounded positions"
         assert torch.equal(export.grid_edges(gs, level).cpu(), pl["edge_index"]), f"level {lv}: coarse edge_index"
         assert_close(nodes["x"].cpu(), pl["x"], what=f"level {lv} pooled features")
+        if not bool(same.all()):
+            # a static fixture cannot adopt the product's position at a voxel whose mean lies within float noise of a
+            # pixel boundary (flagged by the oracle when the fixture was made): levels below it are not comparable
+            print(f"level {lv}: {int((~same).sum())} oracle-flagged ambiguous voxel(s) rounded differently; stopping the comparison here")
+            return False
     assert_close(L["inter"]["o4"][L["grids"][2].cnt[:L["grids"][2].cells] > 0].cpu(), o["out3"], what="out3")
     assert_close(L["inter"]["o5"][L["grids"][3].cnt[:L["grids"][3].cells] > 0].cpu(), o["out4"], what="out4")
-    for k, dd in enumerate(L["dense"]):
-        for name in ("cls", "reg", "obj"):
-            assert_close(dd[name].cpu(), o["dense"][k][name], what=f"dense {name}{k + 1}")
+    if dense:
+        for k, dd in enumerate(L["dense"]):
+            for name in ("cls", "reg", "obj"):
+                assert_close(dd[name].cpu(), o["dense"][k][name], what=f"dense {name}{k + 1}")
     assert_close(dec.cpu(), o["decoded"], what="decoded outputs")
+    return True
+
+
+def _check_forward(model, args, data, B, H, W, image=False, mirror_t_quirk=True, check_public=True):
+    """one forward against the oracle run on the same inputs (see _compare_with) + the detections of the public forward."""
+    from oracle.ref_model import RefModel
+    dec = _run_product(model, data, B, H, W, image=image)
+    L = model.engine.last
+    ref = RefModel({k: v.cpu() for k, v in model.state_dict().items()}, args, H, W)
+    kw = {}
+    if image:
+        kw = dict(image_feats=[f.cpu() for f in model.last_image_feats],
+                  image_outs={k: [t.cpu() for t in v] for k, v in model.last_image_outs.items()})
+    o = ref.forward(data.x, data.pos, data.batch, B, pos_hints=_pos_hints(L), mirror_t_quirk=mirror_t_quirk, **kw)
+    assert _compare_with(model, dec, o, hinted=True)
     if not check_public:
         return o
     # detections through the public forward
     dets = model(data.clone().cuda())[0]
+    _assert_same_detections(dets, o["detections"], B)
+    return o
+
+
+def _assert_same_detections(dets, ref, B):
+    """same detection SET per image (boxes / scores 1e-4, labels equal).  Both sides list detections by descending score;
+    candidates whose scores differ by less than fp32 noise may swap places, so rows are matched by nearest box first."""
     assert len(dets) == B
     for b in range(B):
-        rb = o["detections"][b]
-        assert len(dets[b]["boxes"]) == len(rb["boxes"]), f"image {b}: #detections"
-        if len(rb["boxes"]):
-            assert torch.equal(dets[b]["labels"].cpu(), rb["labels"])
-            assert_close(dets[b]["boxes"].cpu(), rb["boxes"], what="boxes")
-            assert_close(dets[b]["scores"].cpu(), rb["scores"], what="scores")
-    return o
+        rb = ref[b]
+        n = len(rb["boxes"])
+        assert len(dets[b]["boxes"]) == n, f"image {b}: #detections {len(dets[b]['boxes'])} vs {n}"
+        if n == 0:
+            continue
+        mine = torch.cat([dets[b]["boxes"].cpu().float(), dets[b]["scores"].cpu().float().view(-1, 1)], 1)
+        want = torch.cat([rb["boxes"].float(), rb["scores"].float().view(-1, 1)], 1)
+        scale = want.abs().amax(0, keepdim=True).clamp(min=1e-6)
+        cost = ((mine[None] - want[:, None]) / scale).abs().amax(-1)          # [n_ref, n_mine]
+        pick = cost.argmin(1)
+        assert len(set(pick.tolist())) == n, f"image {b}: detections do not match one to one"
+        assert int((pick != torch.arange(n)).sum()) <= n // 4 + 2, f"image {b}: score order differs beyond near-ties"
+        assert torch.equal(dets[b]["labels"].cpu()[pick], rb["labels"])
+        assert_close(mine[pick, :4], want[:, :4], what="boxes")
+        assert_close(mine[pick, 4], want[:, 4], what="scores")
 
 
 @pytest.mark.parametrize("W,H,B,n,kind,size,dataset", FWD_CASES)
@@ -294,6 +327,29 @@ def test_forward_parity_vs_oracle(W, H, B, n, kind, size, dataset):
     model.cuda()
     raw, data = make_inputs(B, n, W, H, seed=31, kind=kind, ragged=True)
     _check_forward(model, args, data, B, H, W)
+
+
+@pytest.mark.parametrize("name", REFERENCE_FIXTURES)
+def test_cuda_path_equals_the_references_own_forward(name):
+    """tests/golden/reference_forward_*.npz: outputs of the reference's UNMODIFIED DAGR.forward (its own net.py, dagr.py,
+    pooling.py, spline_conv.py LUT path, model/utils.py post-processing with torchvision NMS; third-party packages
+    stood in for by tests/golden/ref_shim.py).  No oracle code runs in this test."""
+    from tests.helpers import image_branch_cpu, load_reference_fixture
+    model, args, data, exp, meta = load_reference_fixture(name)
+    W, H, B = meta["W"], meta["H"], meta["B"]
+    feats = outs = None
+    if meta["use_image"]:
+        feats, outs = image_branch_cpu(model, data)                     # dense trunk: fp32 on the CPU, as upstream ran it
+        feats = [f.cuda() for f in feats]
+        outs = {k: [t.cuda() for t in v] for k, v in outs.items()}
+    model.cuda()
+    dec = _run_product(model, data, B, H, W, image_feats=feats, image_outs=outs)
+    complete = _compare_with(model, dec, exp, hinted=False, dense=not meta["use_image"])
+    if complete:
+        det, ndet = model.engine.postprocess(dec.clone(), model.conf_threshold, model.nms_threshold, W, H)
+        torch.cuda.synchronize()
+        dets = [dict(boxes=det[b, :int(ndet[b]), :4], scores=det[b, :int(ndet[b]), 4], labels=det[b, :int(ndet[b]), 5].long()) for b in range(B)]
+        _assert_same_detections(dets, exp["detections"], B)
 
 
 # the BENCHMARKED regime (BASELINE.json configs[1]: dagr-s, 640x480, 300k events per sample in a 50 ms window): mean
@@ -349,36 +405,12 @@ def test_last_event_at_t_equals_T_quirk_h3a():
 def test_image_fusion_parity_vs_oracle(W, H, B, n, size):
     """use_image: sampled ResNet features enter every Layer input and every pooling, CNN head maps are added to the
     dense outputs.  The dense trunk is torch/cuDNN on both sides (its tensors are handed to the oracle)."""
-    from dagr_b200 import export
     from dagr_b200.data import format_data, synth_batch
-    from oracle.ref_model import RefModel
-    model, args = make_model(size, H, W, use_image=True, img_net="resnet18")
+    model, args = make_model(size, H, W, use_image=True, img_net="resnet18", batch_size=B)
     model.cuda()
     raw = synth_batch(B, n, W, H, seed=77, kind="clustered", with_image=True, ragged=True)
     data = format_data(raw.clone())
-    d = data.clone().cuda()
-    model.engine.keep_node_features = True
-    dec = model.forward_decoded(d)
-    torch.cuda.synchronize()
-    L = model.engine.last
-    feats = [f.cpu() for f in model.last_image_feats]
-    outs = {k: [t.cpu() for t in v] for k, v in model.last_image_outs.items()}
-    ref = RefModel({k: v.cpu() for k, v in model.state_dict().items()}, args, H, W)
-    o = ref.forward(data.x, data.pos, data.batch, B, image_feats=feats, image_outs=outs)
-    assert torch.equal(model.engine.export_edges().cpu(), o["edge_index"])
-    N = L["N"]
-    assert_close(export.unsort_rows(model.engine.xa_rows(), L["ws"]["perm"], N).cpu(), o["x1a"], what="conv_block1.conv_block1 (image)")
-    assert_close(export.unsort_rows(L["x1"], L["ws"]["perm"], N).cpu(), o["x1"], what="conv_block1 (image)")
-    geom = L["geom"]
-    for lv in range(4):
-        pl = o["levels"][lv]
-        nodes = export.grid_nodes(L["grids"][lv], geom.levels[lv], geom)
-        same = nodes["pos"].cpu() == pl["pos"][:, :2]
-        assert bool(same[~pl["ambiguous"]].all())
-        assert_close(nodes["x"].cpu(), pl["x"], what=f"level {lv} pooled features (image)")
-        if not bool(same.all()):
-            pytest.skip("pooled position differs only at oracle-flagged ambiguous voxels")
-    assert_close(dec.cpu(), o["decoded"], what="decoded outputs (image)")
+    _check_forward(model, args, data, B, H, W, image=True, check_public=False)
 
 
 @pytest.mark.parametrize("W,H,B,n,chunks", [(240, 180, 1, 8000, [7999, 1]), (640, 480, 2, 30000, [0.5, 0.2, 0.2, 0.1])])
@@ -468,22 +500,11 @@ def test_forward_vs_committed_golden_fixture():
 
 def test_keep_temporal_ordering_filters_coarse_edges_like_the_reference():
     """--keep_temporal_ordering (pooling.py:69-72): coarse edges survive only if t_max[dst] > t_max[src]."""
-    from dagr_b200 import export
-    from oracle.ref_model import RefModel
     W, H, B = 240, 180, 2
-    model, args = make_model("n", H, W, keep_temporal_ordering=True)
+    model, args = make_model("n", H, W, keep_temporal_ordering=True, batch_size=B)
     model.cuda()
     raw, data = make_inputs(B, 4000, W, H, seed=17, kind="clustered")
-    dec, _, _ = _run_graph(model, data, B)
-    L = model.engine.last
-    o = RefModel({k: v.cpu() for k, v in model.state_dict().items()}, args, H, W).forward(data.x, data.pos, data.batch, B)
-    for lv in range(4):
-        pl = o["levels"][lv]
-        nodes = export.grid_nodes(L["grids"][lv], L["geom"].levels[lv], L["geom"])
-        if not bool((nodes["pos"].cpu() == pl["pos"][:, :2]).all()):
-            pytest.skip("ambiguous pooled position")
-        assert torch.equal(export.grid_edges(L["grids"][lv], L["geom"].levels[lv]).cpu(), pl["edge_index"]), f"level {lv}"
-    assert_close(dec.cpu(), o["decoded"], what="decoded (keep_temporal_ordering)")
+    _check_forward(model, args, data, B, H, W)
 
 
 def test_interframe_growing_windows_like_run_test_interframe():
