@@ -11,8 +11,17 @@
 // Voxels whose neighbourhood does not fit the staging buffer fall back to probing global memory.
 #include "common.cuh"
 
-#define BL_THREADS 160           // >= events of a voxel at the nominal density (Poisson mean 134): one pass
-#define BL_CAP 2048              // staged neighbourhood records per CTA (uniform 300k events/sample: ~1200)
+// Two instances of the per-voxel routine (template parameters CAP = staged neighbourhood records, THREADS = CTA size):
+//   regular : one CTA per pool1 voxel, 160 threads (>= events of a voxel at the nominal density, Poisson mean 134: one
+//             pass), 2048 staged records (uniform 300k events/sample: ~1200), 4 CTAs per SM;
+//   dense   : voxels whose 3x3 neighbourhood holds more records than that (moving edges in real / clustered streams: 58 %
+//             of the events of the clustered benchmark stream) are pushed on a device work list by the regular kernel and
+//             processed by a persistent second kernel (one 512-thread CTA per SM, 12288 staged records, dynamic pop) --
+//             the global-memory probe remains only as the fallback behind that.
+#define BL_THREADS 160
+#define BL_CAP 2048
+#define BL_THREADS_BIG 512
+#define BL_CAP_BIG 12288
 #define BL_NB 8                  // time buckets of width delta_t kept per tile pixel
 
 struct BLTile {
@@ -23,16 +32,16 @@ struct BLTile {
     int maxidx;                  // newest arrival index among the events this launch must process (-1: none)
 };
 
-__host__ __device__ __forceinline__ size_t bl_acc_offset(const dagr_geom_t &g)
+__host__ __device__ __forceinline__ size_t bl_acc_offset(const dagr_geom_t &g, int cap, int threads)
 {
     const size_t TW = g.CW + 2 * g.r, TH = g.CH + 2 * g.r, TP = TW * TH;
-    const size_t o = (size_t)BL_CAP * 12 + TP * 4 + (TW + TH) * 4 + TP * BL_NB * 2 + (size_t)g.ncell * 4 + BL_THREADS * 2 + (TW + TH);
+    const size_t o = (size_t)cap * 12 + TP * 4 + (TW + TH) * 4 + TP * BL_NB * 2 + (size_t)g.ncell * 4 + (size_t)threads * 2 + (TW + TH);
     return (o + 15) / 16 * 16;
 }
-static size_t bl_smem_bytes(const dagr_geom_t *g)
+static size_t bl_smem_bytes(const dagr_geom_t *g, int cap, int threads)
 {
     const size_t TW = g->CW + 2 * g->r, TH = g->CH + 2 * g->r;
-    return bl_acc_offset(*g) + (size_t)(DAGR_ELL - 1) * BL_THREADS * 4 + (size_t)BL_NB * (TW + TH) * 4 + 16;
+    return bl_acc_offset(*g, cap, threads) + (size_t)(DAGR_ELL - 1) * threads * 4 + (size_t)BL_NB * (TW + TH) * 4 + 16;
 }
 
 #define BL_R1 96                 // spiral cells walked one-thread-per-event before unsaturated events are handed
@@ -44,7 +53,7 @@ static size_t bl_smem_bytes(const dagr_geom_t *g)
 // events of similar age (threads are assigned in arrival order) and each tile pixel exposes only the
 // sub-range of its FIFO column that can lie within delta_t of the event (time buckets), so the common
 // iteration touches no record at all.
-template <bool STAGED>
+template <bool STAGED, int THREADS>
 __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p, bool active, const int2 me, int eb, int tidx0,
                                          int c_end, const uint32_t *s_pbin, const uint16_t *s_rng, const short *s_sp2,
                                          const int2 *s_ti, const int2 *__restrict__ ti, uint32_t *s_acc,
@@ -78,7 +87,7 @@ __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p,
                     const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
                     if (o.y < me.y && me.x - o.x <= g.dt_us) {              // ev_graph.cu:64-69
                         // accepted (record, cell) pairs wait in shared memory for phase B (staged mode)
-                        if (STAGED) s_acc[n * BL_THREADS + threadIdx.x] = ((uint32_t)j << 10) | (uint32_t)c;
+                        if (STAGED) s_acc[n * THREADS + threadIdx.x] = ((uint32_t)j << 10) | (uint32_t)c;
                         else { nbr[(int64_t)n * N + p] = j; off[(int64_t)n * N + p] = (uint16_t)c; }
                         n++;
                     }
@@ -96,7 +105,7 @@ __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p,
 // for the two descending legs).  Each lane then visits ONLY its non-empty cells, in spiral order, by clearing
 // the lowest set bit: empty pixels (~2/3 of the window) cost nothing and lanes are no longer held to the
 // warp-wide maximum of per-cell work.  Unsaturated events simply run out of rings (no second phase needed).
-template <bool STAGED>
+template <bool STAGED, int THREADS>
 __device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, int p, bool active, const int2 me, int eb, int tx0, int ty0,
                                                int TW, int TH, const uint32_t *s_pbin, const uint16_t *s_rng, const uint32_t *s_occ_r,
                                                const uint32_t *s_occ_c, const short *s_sp2, const int2 *s_ti, const int2 *__restrict__ ti, uint32_t *s_acc,
@@ -112,7 +121,7 @@ __device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, 
         for (int j = base + hi - 1; j >= base + lo && n < kmax; j--) {     // FIFO order: newest first
             const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
             if (o.y < me.y && me.x - o.x <= g.dt_us) {                      // ev_graph.cu:64-69
-                if (STAGED) s_acc[n * BL_THREADS + threadIdx.x] = ((uint32_t)j << 10) | (uint32_t)c;
+                if (STAGED) s_acc[n * THREADS + threadIdx.x] = ((uint32_t)j << 10) | (uint32_t)c;
                 else { nbr[(int64_t)n * N + p] = j; off[(int64_t)n * N + p] = (uint16_t)c; }
                 n++;
             }
@@ -153,7 +162,7 @@ __device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, 
 
 // Phase 2: warp-cooperative continuation for one unsaturated event: the 32 lanes test 32 consecutive spiral
 // cells at once; an exclusive scan over the lanes' accept counts restores the spiral order and the K cap.
-template <bool STAGED>
+template <bool STAGED, int THREADS>
 __device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, int p, const int2 me, int eb, int tidx0, int c_begin,
                                              int n, const uint32_t *s_pbin, const uint16_t *s_rng, const short *s_sp2,
                                              const int2 *s_ti, const int2 *__restrict__ ti, uint32_t *s_acc, int owner,
@@ -184,7 +193,7 @@ __device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, in
                 const int j = base + hi - 1 - k;
                 const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
                 if (o.y < me.y && me.x - o.x <= g.dt_us) {
-                    if (STAGED) s_acc[slot * BL_THREADS + owner] = ((uint32_t)j << 10) | (uint32_t)c;
+                    if (STAGED) s_acc[slot * THREADS + owner] = ((uint32_t)j << 10) | (uint32_t)c;
                     else { nbr[(int64_t)slot * N + p] = j; off[(int64_t)slot * N + p] = (uint16_t)c; }
                     slot++;
                 }
@@ -195,17 +204,15 @@ __device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, in
     return n;
 }
 
-__global__ void __launch_bounds__(BL_THREADS)
-k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const int2 *__restrict__ ti,
-           const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
-           const __grid_constant__ dagr_l1a_params_t P, const int do_conv, const int min_idx, const int32_t *__restrict__ flags,
-           int32_t *__restrict__ nbr,
-           uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask, float *__restrict__ xa)
+// work list layout (int32): [0] = number of pushed voxels, [1] = pop cursor of the dense kernel, [2..] = voxel ids
+template <int CAP, int THREADS>
+__device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const int32_t *__restrict__ start, const int2 *__restrict__ ti,
+                                         const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
+                                         const dagr_l1a_params_t &P, const int do_conv, const int min_idx, const int32_t *__restrict__ flags,
+                                         int32_t *__restrict__ nbr, uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask,
+                                         float *__restrict__ xa, const int cell, unsigned char *smem_raw, BLTile &T, uint32_t &s_mask,
+                                         int32_t *__restrict__ worklist)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ BLTile T;
-    __shared__ uint32_t s_mask;
-    const int cell = blockIdx.x;
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
     const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
@@ -213,18 +220,18 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
 
     // ---- shared memory carve-up -------------------------------------------------------------------
     const int TWmax = g.CW + 2 * g.r, THmax = g.CH + 2 * g.r, TPmax = TWmax * THmax;
-    int2 *s_ti = (int2 *)smem_raw;                                      // [BL_CAP]
-    float *s_feat = (float *)(s_ti + BL_CAP);                           // [BL_CAP]
-    uint32_t *s_pbin = (uint32_t *)(s_feat + BL_CAP);                   // [TP]  pos << 8 | visible count
+    int2 *s_ti = (int2 *)smem_raw;                                      // [CAP]
+    float *s_feat = (float *)(s_ti + CAP);                              // [CAP]
+    uint32_t *s_pbin = (uint32_t *)(s_feat + CAP);                      // [TP]  pos << 8 | visible count
     float *s_posx = (float *)(s_pbin + TPmax);                          // [TWmax]
     float *s_posy = s_posx + TWmax;                                     // [THmax]
     uint16_t *s_rng = (uint16_t *)(s_posy + THmax);                     // [TP][BL_NB]  lo | hi << 8
     short *s_sp = (short *)(s_rng + TPmax * BL_NB);                     // [ncell]  dx | dy << 8
     short *s_sp2 = s_sp + g.ncell;                                      // [ncell]  dy*TW + dx
-    uint16_t *s_order = (uint16_t *)(s_sp2 + g.ncell);                  // [BL_THREADS]
-    uint32_t *s_acc = (uint32_t *)(smem_raw + bl_acc_offset(g));        // [K-1][BL_THREADS]  record << 10 | cell
-    uint32_t *s_occ_r = s_acc + (DAGR_ELL - 1) * BL_THREADS;            // [BL_NB][THmax] row occupancy bitmasks
-    unsigned char *s_colv = (unsigned char *)(s_order + BL_THREADS);    // [TWmax]
+    uint16_t *s_order = (uint16_t *)(s_sp2 + g.ncell);                  // [THREADS]
+    uint32_t *s_acc = (uint32_t *)(smem_raw + bl_acc_offset(g, CAP, THREADS));   // [K-1][THREADS]  record << 10 | cell
+    uint32_t *s_occ_r = s_acc + (DAGR_ELL - 1) * THREADS;               // [BL_NB][THmax] row occupancy bitmasks
+    unsigned char *s_colv = (unsigned char *)(s_order + THREADS);       // [TWmax]
     unsigned char *s_rowv = s_colv + TWmax;                             // [THmax]
 
     const int dtw = max(g.dt_us, 1);
@@ -248,7 +255,13 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
     const int TW = T.TW, TH = T.TH, TP = TW * TH;
     uint32_t *s_occ_c = s_occ_r + BL_NB * TH;                           // [BL_NB][TW] column occupancy bitmasks
     const int total = T.run_off[2] + T.run_len[2];
-    const bool staged = total <= BL_CAP;                                // block-uniform
+    const bool staged = total <= CAP;                                   // block-uniform
+    if (!staged && worklist != nullptr) {
+        // too many records for this instance's staging buffer: hand the voxel to the dense kernel (which runs next on
+        // the stream) instead of probing global memory
+        if (threadIdx.x == 0) worklist[2 + atomicAdd(&worklist[0], 1)] = cell;
+        return;
+    }
     const int bbase = b * per * g.CP;
 
     for (int i = threadIdx.x; i < g.ncell; i += blockDim.x) {
@@ -394,11 +407,11 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         int n;
         const int tidx0 = ty0 * TW + tx0;
         if (use_rings) {
-            if (staged) bl_probe_rings<true>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_sp2, s_ti, ti, s_acc, nbr, off, n);
-            else        bl_probe_rings<false>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+            if (staged) bl_probe_rings<true, THREADS>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+            else        bl_probe_rings<false, THREADS>(g, N, p, active, me, eb, tx0, ty0, TW, TH, s_pbin, s_rng, s_occ_r, s_occ_c, s_sp2, s_ti, ti, s_acc, nbr, off, n);
         } else {
-            if (staged) bl_probe<true>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
-            else        bl_probe<false>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+            if (staged) bl_probe<true, THREADS>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
+            else        bl_probe<false, THREADS>(g, N, p, active, me, eb, tidx0, BL_R1 < g.ncell ? BL_R1 : g.ncell, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, nbr, off, n);
             // events still unsaturated after BL_R1 cells continue warp-cooperatively (32 cells per step), one at a time
             if (BL_R1 < g.ncell) {
                 unsigned todo = __ballot_sync(0xffffffffu, active && n < g.K - 1);
@@ -410,8 +423,8 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
                     const int eeb = __shfl_sync(0xffffffffu, eb, src), etidx = __shfl_sync(0xffffffffu, tidx0, src);
                     const int en = __shfl_sync(0xffffffffu, n, src);
                     const int owner = (int)(threadIdx.x & ~31u) + src;
-                    const int nn = staged ? bl_probe_coop<true>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off)
-                                          : bl_probe_coop<false>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off);
+                    const int nn = staged ? bl_probe_coop<true, THREADS>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off)
+                                          : bl_probe_coop<false, THREADS>(g, N, ep, eme, eeb, etidx, BL_R1, en, s_pbin, s_rng, s_sp2, s_ti, ti, s_acc, owner, nbr, off);
                     if ((int)(threadIdx.x & 31) == src) n = nn;
                 }
                 __syncwarp();
@@ -430,7 +443,7 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
         for (int q = 0; q < nmax; q++) {
             if (q < n) {
                 int j, c;
-                if (staged) { const uint32_t a = s_acc[q * BL_THREADS + threadIdx.x]; j = (int)(a >> 10); c = (int)(a & 0x3ff); }
+                if (staged) { const uint32_t a = s_acc[q * THREADS + threadIdx.x]; j = (int)(a >> 10); c = (int)(a & 0x3ff); }
                 else { j = nbr[(int64_t)q * N + p]; c = off[(int64_t)q * N + p]; }
                 const int sp = s_sp[c];
                 const int tx = tx0 + (int)(signed char)(sp & 0xff), ty = ty0 + (sp >> 8);
@@ -492,10 +505,48 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
 
 
 
+__global__ void __launch_bounds__(BL_THREADS)
+k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const int2 *__restrict__ ti,
+           const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
+           const __grid_constant__ dagr_l1a_params_t P, const int do_conv, const int min_idx, const int32_t *__restrict__ flags,
+           int32_t *__restrict__ nbr, uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask, float *__restrict__ xa,
+           int32_t *__restrict__ worklist)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ BLTile T;
+    __shared__ uint32_t s_mask;
+    bl_voxel<BL_CAP, BL_THREADS>(g, N, start, ti, xyb, feat_s, tab, P, do_conv, min_idx, flags, nbr, off, cellmask, xa,
+                                 (int)blockIdx.x, smem_raw, T, s_mask, worklist);
+}
+
+// dense voxels: persistent CTAs (one per SM) pop voxel ids from the work list the regular kernel filled
+__global__ void __launch_bounds__(BL_THREADS_BIG, 1)
+k_l1_build_dense(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const int2 *__restrict__ ti,
+                 const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
+                 const __grid_constant__ dagr_l1a_params_t P, const int do_conv, const int min_idx, const int32_t *__restrict__ flags,
+                 int32_t *__restrict__ nbr, uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask, float *__restrict__ xa,
+                 int32_t *__restrict__ worklist)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ BLTile T;
+    __shared__ uint32_t s_mask;
+    __shared__ int s_next;
+    const int count = worklist[0];
+    for (;;) {
+        __syncthreads();                                                // everyone is done with the previous voxel
+        if (threadIdx.x == 0) s_next = atomicAdd(&worklist[1], 1);
+        __syncthreads();
+        const int i = s_next;
+        if (i >= count) break;
+        bl_voxel<BL_CAP_BIG, BL_THREADS_BIG>(g, N, start, ti, xyb, feat_s, tab, P, do_conv, min_idx, flags, nbr, off, cellmask, xa,
+                                             worklist[2 + i], smem_raw, T, s_mask, nullptr);
+    }
+}
+
 extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
                              const uint32_t *xyb, const float *feat_s, const float *tab,
                              const dagr_l1a_params_t *p_host, const int32_t *flags, int min_idx, int32_t *nbr, uint16_t *off,
-                             uint32_t *cellmask, float *xa, void *stream)
+                             uint32_t *cellmask, float *xa, int32_t *worklist, void *stream)
 {
     DAGR_CHECK_ARG(g, "null argument");
     static const dagr_l1a_params_t zero_params = {};
@@ -505,11 +556,25 @@ extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *sta
     DAGR_CHECK_ARG(g->r >= 0 && g->r <= 15 && g->Q <= 255, "radius must be <= 15 px and max_queue_size <= 255");
     DAGR_CHECK_ARG(N < (1ll << 24), "the staged probe packs positions in 24 bits (N < 16.7M per call)");
     const int cells = g->B * g->ny1 * g->nx1;
-    const size_t smem = bl_smem_bytes(g);
+    const size_t smem = bl_smem_bytes(g, BL_CAP, BL_THREADS);
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     k_l1_build<<<cells, BL_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab, *p_host,
-                                                                  do_conv, min_idx, flags, nbr, off, cellmask, xa);
+                                                                  do_conv, min_idx, flags, nbr, off, cellmask, xa, worklist);
     DAGR_CHECK_LAUNCH();
+    if (worklist != nullptr) {
+        const size_t smem_big = bl_smem_bytes(g, BL_CAP_BIG, BL_THREADS_BIG);
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            DAGR_CUDA(cudaGetDevice(&dev));
+            DAGR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        DAGR_CUDA(cudaFuncSetAttribute(k_l1_build_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+        k_l1_build_dense<<<n_sm, BL_THREADS_BIG, smem_big, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab,
+                                                                                    *p_host, do_conv, min_idx, flags, nbr, off,
+                                                                                    cellmask, xa, worklist);
+        DAGR_CHECK_LAUNCH();
+    }
     return DAGR_OK;
 }

@@ -306,9 +306,16 @@ extern "C" int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32
 // then hit shared memory.  The per-voxel channel max, mean position and pixel rounding of pool1
 // (pooling.py:66-86) are finished in the same CTA, so neither the per-node activations nor a separate
 // finalize pass touch HBM.  Voxels whose neighbourhood exceeds the staging buffer gather from global.
+// Two instances (template parameters CAP = staged half-rows of 32 B, THREADS = CTA size), like the build kernel:
+//   regular : one CTA per voxel, 160 threads, 1344 rows (43 KB), 4 CTAs per SM;
+//   dense   : voxels whose 3x3 neighbourhood holds more rows (75 % of the events of the clustered benchmark stream) are
+//             queued by the regular kernel and processed by persistent 384-thread CTAs (one per SM) that stage up to
+//             6144 rows (196 KB); only beyond that rows are gathered from global memory / L2.
 #define CB2_THREADS 160
-#define CB2_CAP 1344             // staged half-rows (32 B each) per CTA
-static_assert(2 * CB2_CAP <= 4096, "the ELL word keeps 2*row+swizzle in 12 bits");
+#define CB2_CAP 1344
+#define CB2_THREADS_BIG 384
+#define CB2_CAP_BIG 6144
+static_assert(2 * CB2_CAP_BIG <= 16384, "the ELL word keeps 2*row+swizzle in 14 bits");
 #define CB2_G 5                  // spline slots per pass: one x-slot k, all five y-slots (u = k + 3 j)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -355,7 +362,7 @@ struct CB2Tile {
 // s_ell[q][tid]: see the staged loop below (byte offsets of the row chunks and of the two factor-table rows).
 // Variants measured on B200 and rejected (profiles/r01_conv_b_variants.md): 15 slots x 8 channels per pass (120
 // accumulators, 2 CTAs/SM), 15 slots x 4 channels, phase-2 weights from shared memory or half/half.
-template <bool STAGED, int half, int grp, class PT>
+template <bool STAGED, int half, int grp, int THREADS, class PT>
 __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *__restrict__ xa, const float *s_rows,
                                          const float *s_wx, const float4 *s_wy, const uint32_t *s_ell, const uint16_t *s_sp,
                                          const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
@@ -377,8 +384,8 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
         }                                                                                                           \
     } while (0)
     if constexpr (STAGED) {
-        // the ELL word carries ready-made BYTE offsets: bits 4..15 = 16 * (2 * row + row swizzle) (first 16-byte chunk of
-        // the staged half-row; the other chunk is that offset ^ 16), bits 16..20 = dx + r, bits 21..25 = dy + r.  Slot 0 is
+        // the ELL word carries ready-made BYTE offsets: bits 4..17 = 16 * (2 * row + row swizzle) (first 16-byte chunk of
+        // the staged half-row; the other chunk is that offset ^ 16), bits 18..22 = dx + r, bits 23..27 = dy + r.  Slot 0 is
         // the self loop.  Every instruction costs an issue slot (one per cycle and SMSP) and the loop is issue bound, so
         // the 8 shifts/masks/adds this saves per edge and pass were worth 9 % of the kernel (profiles/r01_ubench_pipes.txt).
         const char *rb = reinterpret_cast<const char *>(s_rows);
@@ -389,8 +396,8 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
         constexpr int kUnroll = CB2_UNROLL;
 #pragma unroll kUnroll
         for (int q = 0; q <= n; q++) {
-            const uint32_t ell = s_ell[q * CB2_THREADS + tix];
-            const uint32_t ro = ell & 0xfff0u, xo = (ell >> 12) & 0x1f0u, yo = (ell >> 16) & 0x3e0u;
+            const uint32_t ell = s_ell[q * THREADS + tix];
+            const uint32_t ro = ell & 0x3fff0u, xo = (ell >> 14) & 0x1f0u, yo = (ell >> 18) & 0x3e0u;
             const float4 t0 = *reinterpret_cast<const float4 *>(rb + ro), t1 = *reinterpret_cast<const float4 *>(rb + (ro ^ 16u));
             const float wx = *reinterpret_cast<const float *>(wxb + xo);
             const float4 wya = *reinterpret_cast<const float4 *>(wyb + yo);
@@ -454,28 +461,40 @@ __device__ __forceinline__ int cb2_round_to_pixel(float mean, int size)
 // 8-channel chunks, skip + act + pool1 epilogue); <dagr_l1img_params_t, 3, true> is the image-fusion variant of
 // conv_block1.conv_block1 (1 + 16 + 2 input channels padded to 3 chunks; epilogue = BN + act, rows written back
 // chunk-major for conv_block2, plus the layer's skip branch BN(Linear(x0)) -> skip_out; no pooling).
-template <class PT, int NCH, bool MODE_A>
-__global__ void __launch_bounds__(CB2_THREADS, MODE_A ? 3 : 4)
-k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
+template <int THREADS>
+struct CB2Shared {
+    CB2Tile T;
+    uint64_t bar;
+    float red[THREADS / 32][16];
+    long long sum[THREADS / 32][3];
+    int tm[THREADS / 32];
+};
+
+// The per-voxel routine is a template over the input rows: <dagr_l1b_params_t, 2, false> is conv_block2 (16 channels = 2
+// staged 8-channel chunks, skip + act + pool1 epilogue); <dagr_l1img_params_t, 3, true> is the image-fusion variant of
+// conv_block1.conv_block1 (1 + 16 + 2 input channels padded to 3 chunks; epilogue = BN + act, rows written back
+// chunk-major for conv_block2, plus the layer's skip branch BN(Linear(x0)) -> skip_out; no pooling).
+// work list layout (int32): [0] = number of queued voxels, [1] = pop cursor of the dense kernel, [2..] = voxel ids
+template <class PT, int NCH, bool MODE_A, int CAP, int THREADS>
+__device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
              const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
-             const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off, const float *__restrict__ tab,
-             const __grid_constant__ PT P, const float *__restrict__ skip_pre, const int min_idx,
+             const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
+             const PT &P, const float *__restrict__ skip_pre, const int min_idx,
              float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
              float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx,
-             float *__restrict__ xa_out, float *__restrict__ skip_out)
+             float *__restrict__ xa_out, float *__restrict__ skip_out,
+             const int cell, unsigned char *smem_raw, CB2Shared<THREADS> &S, uint32_t &parity, int32_t *__restrict__ worklist)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ CB2Tile T;
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_red[CB2_THREADS / 32][16];
-    __shared__ long long s_sum[CB2_THREADS / 32][3];
-    __shared__ int s_tm[CB2_THREADS / 32];
-    float *s_rows = (float *)smem_raw;                                   // [CB2_CAP][8]   one channel half of the 3 runs
-    float *s_wx = s_rows + (size_t)CB2_CAP * 8;                          // [2r+1][4]   x factor of the slot weights
+    CB2Tile &T = S.T;
+    uint64_t &s_bar = S.bar;
+    auto &s_red = S.red;
+    auto &s_sum = S.sum;
+    auto &s_tm = S.tm;
+    float *s_rows = (float *)smem_raw;                                   // [CAP][8]   one channel half of the 3 runs
+    float *s_wx = s_rows + (size_t)CAP * 8;                              // [2r+1][4]   x factor of the slot weights
     float4 *s_wy = (float4 *)(s_wx + 128);                               // [2r+1][2]   y factor
-    uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [16][CB2_THREADS]  slot 0 = self loop
-    uint16_t *s_sp = (uint16_t *)(s_ell + DAGR_ELL * CB2_THREADS);       // [ncell]  (dx + r) | (dy + r) << 5
-    const int cell = blockIdx.x;
+    uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [16][THREADS]  slot 0 = self loop
+    uint16_t *s_sp = (uint16_t *)(s_ell + DAGR_ELL * THREADS);           // [ncell]  (dx + r) | (dy + r) << 5
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
     const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
@@ -501,7 +520,6 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             if (lane == 0) { T.run_start[k] = ok ? s0 : 0; T.run_len[k] = ok ? e0 - s0 : 0; T.run_off[k] = o; }
             o += ok ? e0 - s0 : 0;
         }
-        if (lane == 0) mbar_init(&s_bar, 1);
     }
     for (int i = threadIdx.x; i < 2 * g.r + 1; i += blockDim.x) {
         reinterpret_cast<float4 *>(s_wx)[i] = __ldg(reinterpret_cast<const float4 *>(g.tabx) + i);
@@ -512,7 +530,12 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
         s_sp[i] = (uint16_t)(((int)g.spiral[2 * i] + g.r) | (((int)g.spiral[2 * i + 1] + g.r) << 5));
     __syncthreads();
     const int total = T.run_off[2] + T.run_len[2];
-    const bool staged = total <= CB2_CAP;                                // block-uniform
+    const bool staged = total <= CAP;                                    // block-uniform
+    if (!staged && worklist != nullptr) {
+        // more rows than this instance can stage: queue the voxel for the dense kernel (next launch on the stream)
+        if (threadIdx.x == 0) worklist[2 + atomicAdd(&worklist[0], 1)] = cell;
+        return;
+    }
     const int s1 = T.run_start[1];
     const int s2 = T.run_len[2] > 0 ? T.run_start[2] : 0x7fffffff;
     const int d0 = T.run_off[0] - T.run_start[0], d1 = T.run_off[1] - T.run_start[1], d2 = T.run_off[2] - T.run_start[2];
@@ -522,7 +545,6 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     for (int c = 0; c < 16; c++) m[c] = -INFINITY;
     long long sx = 0, sy = 0, st = 0;
     int tm = -2147483647;
-    uint32_t parity = 0;
     // Sparse voxels (at most one warp of nodes, e.g. the early windows of an inter-frame sequence): the per-thread chain of
     // six passes is the whole run time of the CTA and four of its five warps would idle.  Warps 0..2 then share the SAME
     // nodes and take one x-slot each (both channel halves), their partial sums are added through shared memory: a third of
@@ -554,9 +576,9 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
             for (int q = 0; q < DAGR_ELL - 1; q++) {
                 const int j = jj[q];
                 const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
-                s_ell[(q + 1) * CB2_THREADS + tix] = ((uint32_t)(2 * row + XA_SWZ(j)) << 4) | ((uint32_t)s_sp[cc[q]] << 16);
+                s_ell[(q + 1) * THREADS + tix] = ((uint32_t)(2 * row + XA_SWZ(j)) << 4) | ((uint32_t)s_sp[cc[q]] << 18);
             }
-            s_ell[tix] = ((uint32_t)(2 * (p + d1) + XA_SWZ(p)) << 4) | ((uint32_t)(g.r | (g.r << 5)) << 16);   // self loop
+            s_ell[tix] = ((uint32_t)(2 * (p + d1) + XA_SWZ(p)) << 4) | ((uint32_t)(g.r | (g.r << 5)) << 18);   // self loop
         }
         float2 o2[8], sk2[MODE_A ? 8 : 1];
 #pragma unroll
@@ -607,8 +629,8 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
 #undef CB2_ROOT
 #define CB2_PASS(H, G)                                                                                               \
     do {                                                                                                            \
-        if (staged) cb2_pass<true, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2); \
-        else        cb2_pass<false, H, G>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, tix, o2);     \
+        if (staged) cb2_pass<true, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2); \
+        else        cb2_pass<false, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, tix, o2);     \
     } while (0)
 #define CB2_HALF(H)                                                                                                  \
     do {                                                                                                            \
@@ -752,43 +774,115 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     }
 }
 
+
+template <class PT, int NCH, bool MODE_A>
+__global__ void __launch_bounds__(CB2_THREADS, MODE_A ? 3 : 4)
+k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
+             const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
+             const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
+             const __grid_constant__ PT P, const float *__restrict__ skip_pre, const int min_idx,
+             float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
+             float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx,
+             float *__restrict__ xa_out, float *__restrict__ skip_out, int32_t *__restrict__ worklist)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) CB2Shared<CB2_THREADS> S;
+    if (threadIdx.x == 0) mbar_init(&S.bar, 1);                         // made visible by the routine's first __syncthreads
+    uint32_t parity = 0;
+    cb2_voxel<PT, NCH, MODE_A, CB2_CAP, CB2_THREADS>(g, N, start, xyb, ti, feat_s, xa, nbr, off, P, skip_pre, min_idx, persist, x1, cnt, pxy,
+                                                      tmean, tmax, xg, ldx, xa_out, skip_out, (int)blockIdx.x, smem_raw, S, parity, worklist);
+}
+
+// dense voxels: persistent CTAs (one per SM) pop voxel ids from the work list the regular kernel filled
+template <class PT, int NCH, bool MODE_A>
+__global__ void __launch_bounds__(CB2_THREADS_BIG, 1)
+k_l1_conv_b2_dense(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
+                   const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
+                   const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
+                   const __grid_constant__ PT P, const float *__restrict__ skip_pre, const int min_idx,
+                   float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
+                   float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx,
+                   float *__restrict__ xa_out, float *__restrict__ skip_out, int32_t *__restrict__ worklist)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) CB2Shared<CB2_THREADS_BIG> S;
+    __shared__ int s_next;
+    if (threadIdx.x == 0) mbar_init(&S.bar, 1);
+    uint32_t parity = 0;                                                // the barrier's phase carries over from voxel to voxel
+    const int count = worklist[0];
+    for (;;) {
+        __syncthreads();                                                // everyone is done with the previous voxel
+        if (threadIdx.x == 0) s_next = atomicAdd(&worklist[1], 1);
+        __syncthreads();
+        const int i = s_next;
+        if (i >= count) break;
+        cb2_voxel<PT, NCH, MODE_A, CB2_CAP_BIG, CB2_THREADS_BIG>(g, N, start, xyb, ti, feat_s, xa, nbr, off, P, skip_pre, min_idx, persist, x1,
+                                                                  cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, worklist[2 + i],
+                                                                  smem_raw, S, parity, nullptr);
+    }
+}
+
+static size_t cb2_smem_bytes(const dagr_geom_t *g, int cap, int threads)
+{
+    return (size_t)cap * 32 + 96 * 16 + (size_t)DAGR_ELL * threads * 4 + (size_t)g->ncell * 2 + 32;
+}
+
+template <class PT, int NCH, bool MODE_A>
+static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb, const int2 *ti, const float *feat_s,
+                      const float *xa, const int32_t *nbr, const uint16_t *off, const PT *p_host, const float *skip_pre, int min_idx,
+                      float *persist, float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg, int ldx,
+                      float *xa_out, float *skip_out, int32_t *worklist, cudaStream_t st)
+{
+    const int cells = g->B * g->ny1 * g->nx1;
+    const size_t smem = cb2_smem_bytes(g, CB2_CAP, CB2_THREADS);
+    auto kern = k_l1_conv_b2<PT, NCH, MODE_A>;
+    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<cells, CB2_THREADS, smem, st>>>(*g, N, start, xyb, ti, feat_s, xa, nbr, off, *p_host, skip_pre, min_idx, persist, x1, cnt, pxy,
+                                           tmean, tmax, xg, ldx, xa_out, skip_out, worklist);
+    DAGR_CHECK_LAUNCH();
+    if (worklist != nullptr) {
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            DAGR_CUDA(cudaGetDevice(&dev));
+            DAGR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const size_t smem_big = cb2_smem_bytes(g, CB2_CAP_BIG, CB2_THREADS_BIG);
+        auto kd = k_l1_conv_b2_dense<PT, NCH, MODE_A>;
+        DAGR_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+        kd<<<n_sm, CB2_THREADS_BIG, smem_big, st>>>(*g, N, start, xyb, ti, feat_s, xa, nbr, off, *p_host, skip_pre, min_idx, persist, x1,
+                                                    cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, worklist);
+        DAGR_CHECK_LAUNCH();
+    }
+    return DAGR_OK;
+}
+
 extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
                                          const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
                                          const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
                                          const float *skip_pre, int min_idx, float *persist, float *x1, int32_t *cnt,
-                                         int32_t *pxy, float *tmean, float *tmax, float *xg, int ldx, void *stream)
+                                         int32_t *pxy, float *tmean, float *tmax, float *xg, int ldx, int32_t *worklist, void *stream)
 {
+    (void)tab;
     DAGR_CHECK_ARG(g && p_host, "null argument");
-    const int cells = g->B * g->ny1 * g->nx1;
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
-    const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)DAGR_ELL * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
-    auto kern = k_l1_conv_b2<dagr_l1b_params_t, 2, false>;
-    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    kern<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, tab, *p_host,
-                                                              skip_pre, min_idx, persist, x1, cnt, pxy, tmean, tmax, xg, ldx,
-                                                              nullptr, nullptr);
-    DAGR_CHECK_LAUNCH();
-    return DAGR_OK;
+    return cb2_launch<dagr_l1b_params_t, 2, false>(g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, p_host, skip_pre, min_idx,
+                                                   persist, x1, cnt, pxy, tmean, tmax, xg, ldx, nullptr, nullptr, worklist,
+                                                   (cudaStream_t)stream);
 }
 
 // image fusion: conv_block1.conv_block1 on the 19-channel rows x0 (chunk-major [3][N][8], chunks swizzled like xa)
 extern "C" int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const float *x0, const int32_t *nbr,
-                                    const uint16_t *off, const dagr_l1img_params_t *p_host, float *xa, float *skipv, void *stream)
+                                    const uint16_t *off, const dagr_l1img_params_t *p_host, float *xa, float *skipv,
+                                    int32_t *worklist, void *stream)
 {
     DAGR_CHECK_ARG(g && p_host, "null argument");
     if (N <= 0) return DAGR_OK;
-    const int cells = g->B * g->ny1 * g->nx1;
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
-    const size_t smem = (size_t)CB2_CAP * 32 + 96 * 16 + (size_t)DAGR_ELL * CB2_THREADS * 4 + (size_t)g->ncell * 2 + 32;
-    auto kern = k_l1_conv_b2<dagr_l1img_params_t, 3, true>;
-    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    kern<<<cells, CB2_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, nullptr, nullptr, nullptr, x0, nbr, off, nullptr, *p_host,
-                                                              nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                              nullptr, 0, xa, skipv);
-    DAGR_CHECK_LAUNCH();
-    return DAGR_OK;
+    return cb2_launch<dagr_l1img_params_t, 3, true>(g, N, start, nullptr, nullptr, nullptr, x0, nbr, off, p_host, nullptr, 0, nullptr,
+                                                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, xa, skipv, worklist,
+                                                    (cudaStream_t)stream);
 }
 
 

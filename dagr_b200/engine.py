@@ -102,6 +102,8 @@ class Engine:
         self.voxel_conv_b = True             # conv_b + pool1 as one CTA per voxel with TMA-staged rows (False: v1)
         self.use_graphs = True               # replay the fixed-shape coarse stack as a CUDA graph
         self.fused_build = True              # probe + conv_a in one shared-memory-tiled kernel (False: v1 split kernels)
+        self.dense_worklists = True          # voxels beyond the per-voxel kernels' staging capacity go to the persistent dense
+                                             # kernels (False: global-memory fallback inside the per-voxel kernels, for A/B tests)
         self.last = {}
         self.launches = 0                    # kernels of libdagr_b200.so enqueued so far
         self.prof = None                     # dict name -> [(start_evt, end_evt)] when per-op timing is on
@@ -116,7 +118,7 @@ class Engine:
         self._out_slot = {}
 
     # kernels enqueued by each C-ABI call (see csrc/*.cu)
-    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=1, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=1, dagr_l1_x0_image=1, dagr_xa_permute=1, dagr_l1_conv_a_image=1, dagr_voxel_sample_max=1,
+    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=2, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=2, dagr_l1_x0_image=1, dagr_xa_permute=1, dagr_l1_conv_a_image=2, dagr_voxel_sample_max=1,
                      dagr_pool1_finalize=1, dagr_grid_cat_pos=1, dagr_grid_conv=1, dagr_grid_linear_bn=1, dagr_grid_pool=1,
                      dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1,
                      dagr_postprocess_nms=1, dagr_sample_features=1, dagr_denormalize_pos=1)
@@ -279,6 +281,8 @@ class Engine:
                 take(f"ptmax{lv}", cells * 4)
                 take(f"pcnt{lv}", cells * 4)
                 take(f"pmask{lv}", cells * 4)
+            for wl in ("wl_build", "wl_conv_a", "wl_conv_b"):     # dense-voxel work lists: [count, cursor, voxel ids ...]
+                take(wl, (geom.cells1 + 2) * 4)
             take("err", 4)
             take("flags", 16)
             ws["zero_buf"] = torch.zeros(off, dtype=torch.uint8, device=dev)
@@ -452,6 +456,7 @@ class Engine:
             cellmask, persist, min_idx = stream_state.cellmask, stream_state.voxmax, int(n_old)
         poolmax = self._zs(ws, "poolmax", torch.int32)
         flags = self._zs(ws, "flags", torch.int32)
+        wl_build = self._zs(ws, "wl_build", torch.int32) if self.dense_worklists else None
         # ---- event level ---------------------------------------------------------------------
         self._run("graph_sort", lib.dagr_graph_sort, g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ws["key"]),
                                        _lib.ptr(ws["tmp"]), _lib.ptr(ws["count"]), _lib.ptr(ws["blocksums"]),
@@ -462,21 +467,21 @@ class Engine:
             # adjacency only; conv_block1 runs on [polarity, 16 image samples, x, y] (net.py:117-126)
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), None, _lib.ptr(flags), 0, _lib.ptr(nbr), _lib.ptr(off),
-                      _lib.ptr(cellmask), _lib.ptr(ws["xa"]), st)
+                      _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_build), st)
             f0 = image_feats[0]
             x0 = self._buf(ws, "x0img", (3 * max(N, 1) * 8,), torch.float32, dev)
             skipv = self._buf(ws, "skipv", (max(N, 1), 16), torch.float32, dev)
             self._run("l1_x0_image", lib.dagr_l1_x0_image, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(f0),
                       int(f0.shape[2]), int(f0.shape[3]), _lib.ptr(x0), st)
             self._run("l1_conv_a_image", lib.dagr_l1_conv_a_image, g, N, _lib.ptr(ws["start"]), _lib.ptr(x0), _lib.ptr(nbr), _lib.ptr(off),
-                      C.byref(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), st)
+                      C.byref(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), _lib.ptr(self._zs(ws, "wl_conv_a", torch.int32)), st)
         elif self.fused_build or stream_state is not None:
             if min_idx > 0:
                 self._run("xa_gather", lib.dagr_xa_permute, N, _lib.ptr(ws["perm"]), min_idx, _lib.ptr(ws["xa"]),
                           _lib.ptr(stream_state.xa_arr), 0, st)
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(flags), min_idx, _lib.ptr(nbr),
-                      _lib.ptr(off), _lib.ptr(cellmask), _lib.ptr(ws["xa"]), st)
+                      _lib.ptr(off), _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_build), st)
             if stream_state is not None:
                 self._run("xa_scatter", lib.dagr_xa_permute, N, _lib.ptr(ws["perm"]), min_idx, _lib.ptr(ws["xa"]),
                           _lib.ptr(stream_state.xa_arr), 1, st)
@@ -497,7 +502,8 @@ class Engine:
             self._run("l1_conv_b_pool_voxel", lib.dagr_l1_conv_b_pool_voxel, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["ti"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]), _lib.ptr(nbr), _lib.ptr(off),
                       _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(skipv) if use_image else None, min_idx, _lib.ptr(persist),
-                      _lib.ptr(x1), _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean), _lib.ptr(g1.tmax), _lib.ptr(g1.x), c1, st)
+                      _lib.ptr(x1), _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean), _lib.ptr(g1.tmax), _lib.ptr(g1.x), c1,
+                      _lib.ptr(self._zs(ws, "wl_conv_b", torch.int32)) if self.dense_worklists else None, st)
             if use_image:                                     # sampling_skip before pool1 (net.py:128-131)
                 f1 = image_feats[1]
                 self._run("voxel_sample_max", lib.dagr_voxel_sample_max, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(f1),
