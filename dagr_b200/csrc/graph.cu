@@ -130,15 +130,26 @@ extern "C" int dagr_denormalize_pos(const float *pos, int64_t N, int W, int H, i
 // ------------------------------------------------------------------------------------------------
 // sort
 // ------------------------------------------------------------------------------------------------
+// Streaming form (dagr_graph_sort_ring): the events live in a ring buffer of `mask + 1` slots and the live window is
+// described by a DEVICE control block ctl = {head, n}: event i of the window is slot (head + i) & mask, and the launch
+// covers the whole capacity -- so the grid does not depend on the live count and the step can be replayed as a CUDA graph.
+#define RING_N(N) ((ctl != nullptr) ? (int64_t)ctl[1] : (N))
+#define RING_AT(i) ((ctl != nullptr) ? (int64_t)((ctl[0] + (int)(i)) & mask) : (int64_t)(i))
+
 __global__ void k_keys_hist(dagr_geom_t g, const int32_t *__restrict__ batch, const int32_t *__restrict__ pos, int64_t N,
-                            int32_t *__restrict__ key, int32_t *__restrict__ count, int32_t *__restrict__ flags)
+                            int32_t *__restrict__ key, int32_t *__restrict__ count, int32_t *__restrict__ flags,
+                            const int32_t *__restrict__ ctl, int mask)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int x = pos[3 * i], y = pos[3 * i + 1], b = batch[i];
+    if (i >= RING_N(N)) return;
+    const int64_t si = RING_AT(i);
+    int x = pos[3 * si], y = pos[3 * si + 1], b = batch[si];
     // contract check: events are time-sorted within each sample.  If not, flags[0] = 1 and the
     // build kernel disables its time-bucket pruning (results stay exact, only slower).
-    if (flags != nullptr && i > 0 && batch[i - 1] == b && pos[3 * (i - 1) + 2] > pos[3 * i + 2]) flags[0] = 1;
+    if (flags != nullptr && i > 0) {
+        const int64_t sp = RING_AT(i - 1);
+        if (batch[sp] == b && pos[3 * sp + 2] > pos[3 * si + 2]) flags[0] = 1;
+    }
     // out-of-range events are clamped into the grid (the reference would index out of bounds)
     x = min(max(x, 0), g.W - 1); y = min(max(y, 0), g.H - 1); b = min(max(b, 0), g.B - 1);
     int k = b * (g.ny1 * g.nx1 * g.CP) + __ldg(g.ykey + y) + __ldg(g.xkey + x);
@@ -147,10 +158,10 @@ __global__ void k_keys_hist(dagr_geom_t g, const int32_t *__restrict__ batch, co
 }
 
 __global__ void k_scatter(const int32_t *__restrict__ key, int64_t N, const int32_t *__restrict__ start,
-                          int32_t *__restrict__ count, int32_t *__restrict__ tmp)
+                          int32_t *__restrict__ count, int32_t *__restrict__ tmp, const int32_t *__restrict__ ctl)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= RING_N(N)) return;
     int k = key[i];
     int slot = atomicSub(count + k, 1) - 1;          // leaves count[] all-zero again
     tmp[start[k] + slot] = (int)i;
@@ -161,22 +172,46 @@ __global__ void k_rank_emit(dagr_geom_t g, const int32_t *__restrict__ key, cons
                             const int32_t *__restrict__ start, const int32_t *__restrict__ batch,
                             const int32_t *__restrict__ pos, const float *__restrict__ feat,
                             int32_t *__restrict__ perm, int2 *__restrict__ ti, uint32_t *__restrict__ xyb,
-                            float *__restrict__ feat_s)
+                            float *__restrict__ feat_s, const int32_t *__restrict__ ctl, int mask)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
+    if (j >= RING_N(N)) return;
     int i = tmp[j];
     int k = key[i];
     int s = start[k], e = start[k + 1];
     int rank = 0;
     for (int q = s; q < e; q++) rank += (tmp[q] < i);
     int p = s + rank;
-    int x = pos[3 * i], y = pos[3 * i + 1], t = pos[3 * i + 2], b = batch[i];
+    const int64_t si = RING_AT(i);
+    int x = pos[3 * si], y = pos[3 * si + 1], t = pos[3 * si + 2], b = batch[si];
     x = min(max(x, 0), g.W - 1); y = min(max(y, 0), g.H - 1); b = min(max(b, 0), g.B - 1);
     perm[p] = i;
     ti[p] = make_int2(t, i);
     xyb[p] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)b << 24);
-    feat_s[p] = feat[i];
+    feat_s[p] = feat[si];
+}
+
+static int graph_sort_impl(const dagr_geom_t *g, const int32_t *batch, const int32_t *pos, const float *feat,
+                           int64_t N, const int32_t *ctl, int mask, int32_t *key, int32_t *tmp, int32_t *count, int32_t *blocksums,
+                           int32_t *start, int32_t *perm, int32_t *ti, uint32_t *xyb, float *feat_s,
+                           int32_t *flags, void *stream)
+{
+    DAGR_CHECK_ARG(g && g->W <= 4096 && g->H <= 4096 && g->B <= 256, "geometry out of range (W,H<=4096, B<=256)");
+    DAGR_CHECK_ARG(N >= 0 && N < (1ll << 31), "N out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0) {
+        k_keys_hist<<<dagr_div_up(N, 256), 256, 0, st>>>(*g, batch, pos, N, key, count, flags, ctl, mask);
+        DAGR_CHECK_LAUNCH();
+    }
+    scan_exclusive(count, start, g->NK, blocksums, st);      // start[NK] = N
+    DAGR_CHECK_LAUNCH();
+    if (N > 0) {
+        k_scatter<<<dagr_div_up(N, 256), 256, 0, st>>>(key, N, start, count, tmp, ctl);
+        k_rank_emit<<<dagr_div_up(N, 256), 256, 0, st>>>(*g, key, tmp, N, start, batch, pos, feat, perm,
+                                                         (int2 *)ti, xyb, feat_s, ctl, mask);
+        DAGR_CHECK_LAUNCH();
+    }
+    return DAGR_OK;
 }
 
 extern "C" int dagr_graph_sort(const dagr_geom_t *g, const int32_t *batch, const int32_t *pos, const float *feat,
@@ -184,21 +219,70 @@ extern "C" int dagr_graph_sort(const dagr_geom_t *g, const int32_t *batch, const
                                int32_t *start, int32_t *perm, int32_t *ti, uint32_t *xyb, float *feat_s,
                                int32_t *flags, void *stream)
 {
-    DAGR_CHECK_ARG(g && g->W <= 4096 && g->H <= 4096 && g->B <= 256, "geometry out of range (W,H<=4096, B<=256)");
-    DAGR_CHECK_ARG(N >= 0 && N < (1ll << 31), "N out of range");
+    return graph_sort_impl(g, batch, pos, feat, N, nullptr, 0, key, tmp, count, blocksums, start, perm, ti, xyb, feat_s, flags, stream);
+}
+
+extern "C" int dagr_graph_sort_ring(const dagr_geom_t *g, const int32_t *batch, const int32_t *pos, const float *feat,
+                                    int64_t capacity, const int32_t *ctl, int32_t *key, int32_t *tmp, int32_t *count,
+                                    int32_t *blocksums, int32_t *start, int32_t *perm, int32_t *ti, uint32_t *xyb, float *feat_s,
+                                    int32_t *flags, void *stream)
+{
+    DAGR_CHECK_ARG(ctl != nullptr && capacity > 0 && (capacity & (capacity - 1)) == 0, "ring capacity must be a power of two");
+    return graph_sort_impl(g, batch, pos, feat, capacity, ctl, (int)(capacity - 1), key, tmp, count, blocksums, start, perm, ti, xyb,
+                           feat_s, flags, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming window (the idea of the min_index watermark of ev_graph.cu:62 / ev_graph.py:121-136):
+// the live events of ONE stream sit time-sorted in a ring; a step evicts the prefix older than t_cut (O(log n) search,
+// no data movement) and appends the new chunk behind the tail.
+//   ctl   i32[8] : [0] head slot, [1] live count, [2] evicted by the last step, [3] appended by the last step,
+//                  [4] sticky overflow flag (chunk did not fit: oldest events were dropped beyond t_cut), [5] kept count
+//   stage i32[4 + 4*max_chunk] : [0] n_new, [1] t_cut, then (x, y, t, polarity +-1) per new event
+// ------------------------------------------------------------------------------------------------
+__global__ void k_stream_advance(int32_t *__restrict__ ctl, const int32_t *__restrict__ stage, const int32_t *__restrict__ pos,
+                                 int mask, int max_chunk)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int head = ctl[0], n = ctl[1];
+    const int n_new = min(max(stage[0], 0), max_chunk), t_cut = stage[1];
+    int lo = 0, hi = n;
+    while (lo < hi) {                                                   // first live event with t >= t_cut
+        const int mid = (lo + hi) >> 1;
+        if (pos[3 * (int64_t)((head + mid) & mask) + 2] < t_cut) lo = mid + 1; else hi = mid;
+    }
+    int shift = lo;
+    const int cap = mask + 1;
+    if (n - shift + n_new > cap) { shift = n + n_new - cap; ctl[4] = 1; }
+    ctl[0] = (head + shift) & mask;
+    ctl[5] = n - shift;
+    ctl[1] = n - shift + n_new;
+    ctl[2] = shift;
+    ctl[3] = n_new;
+}
+
+__global__ void k_stream_append(const int32_t *__restrict__ ctl, const int32_t *__restrict__ stage, int32_t *__restrict__ batch,
+                                int32_t *__restrict__ pos, float *__restrict__ feat, int mask, int sample)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ctl[3]) return;
+    const int64_t s = (ctl[0] + ctl[5] + j) & mask;
+    const int4 e = reinterpret_cast<const int4 *>(stage + 4)[j];
+    pos[3 * s] = e.x; pos[3 * s + 1] = e.y; pos[3 * s + 2] = e.z;
+    feat[s] = (float)e.w;
+    batch[s] = sample;
+}
+
+extern "C" int dagr_stream_push(int32_t *ctl, const int32_t *stage, int32_t *batch, int32_t *pos, float *feat, int64_t capacity,
+                                int max_chunk, int sample, void *stream)
+{
+    DAGR_CHECK_ARG(ctl && stage && batch && pos && feat, "null argument");
+    DAGR_CHECK_ARG(capacity > 0 && (capacity & (capacity - 1)) == 0 && max_chunk > 0 && max_chunk <= capacity,
+                   "ring capacity must be a power of two >= max_chunk");
     cudaStream_t st = (cudaStream_t)stream;
-    if (N > 0) {
-        k_keys_hist<<<dagr_div_up(N, 256), 256, 0, st>>>(*g, batch, pos, N, key, count, flags);
-        DAGR_CHECK_LAUNCH();
-    }
-    scan_exclusive(count, start, g->NK, blocksums, st);      // start[NK] = N
+    k_stream_advance<<<1, 32, 0, st>>>(ctl, stage, pos, (int)(capacity - 1), max_chunk);
+    k_stream_append<<<dagr_div_up(max_chunk, 256), 256, 0, st>>>(ctl, stage, batch, pos, feat, (int)(capacity - 1), sample);
     DAGR_CHECK_LAUNCH();
-    if (N > 0) {
-        k_scatter<<<dagr_div_up(N, 256), 256, 0, st>>>(key, N, start, count, tmp);
-        k_rank_emit<<<dagr_div_up(N, 256), 256, 0, st>>>(*g, key, tmp, N, start, batch, pos, feat, perm,
-                                                         (int2 *)ti, xyb, feat_s);
-        DAGR_CHECK_LAUNCH();
-    }
     return DAGR_OK;
 }
 

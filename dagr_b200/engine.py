@@ -118,7 +118,7 @@ class Engine:
         self._out_slot = {}
 
     # kernels enqueued by each C-ABI call (see csrc/*.cu)
-    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_search=1, dagr_l1_build=2, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=2, dagr_l1_x0_image=1, dagr_xa_permute=1, dagr_l1_conv_a_image=2, dagr_voxel_sample_max=1,
+    _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_sort_ring=6, dagr_stream_push=2, dagr_graph_search=1, dagr_l1_build=2, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=2, dagr_l1_x0_image=1, dagr_xa_permute=1, dagr_l1_conv_a_image=2, dagr_voxel_sample_max=1,
                      dagr_pool1_finalize=1, dagr_grid_cat_pos=1, dagr_grid_conv=1, dagr_grid_linear_bn=1, dagr_grid_pool=1,
                      dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1,
                      dagr_postprocess_nms=1, dagr_sample_features=1, dagr_denormalize_pos=1)
@@ -416,8 +416,12 @@ class Engine:
 
     @torch.no_grad()
     def forward_events(self, batch_i32: torch.Tensor, pos_i32: torch.Tensor, feat: torch.Tensor, B: int,
-                       W: int, H: int, image_feats=None, image_outs=None, stream_state=None, n_old: int = 0):
-        """batch int32[N], pos int32[N,3], feat fp32[N] (polarity) on CUDA -> decoded [B, A, 5+nc]."""
+                       W: int, H: int, image_feats=None, image_outs=None, stream_state=None, n_old: int = 0, ring=None):
+        """batch int32[N], pos int32[N,3], feat fp32[N] (polarity) on CUDA -> decoded [B, A, 5+nc].
+
+        ring = device control block (int32[8], dagr_graph_sort_ring): the three inputs are ring buffers of N = capacity
+        slots whose live window {head, count} is only known on the device; every launch then covers the capacity, nothing
+        depends on a host-side count and the whole call can sit inside one captured CUDA graph (dagr_b200.streaming)."""
         for n, t in (("batch", batch_i32), ("pos", pos_i32), ("x", feat)):
             _lib.require_cuda(t, n)
         dev = pos_i32.device
@@ -425,7 +429,7 @@ class Engine:
         geom = self.geometry(W, H, B, dev)
         pk = self.pack(geom, dev)
         ws = self.workspace(geom, N, dev)
-        ov = bool(self.overlap and stream_state is None and image_feats is None and self.prof is None and self.use_graphs)
+        ov = bool(self.overlap and stream_state is None and image_feats is None and self.prof is None and self.use_graphs and ring is None)
         slot = 0
         if ov:
             slot, self._slot = self._slot, self._slot ^ 1
@@ -458,10 +462,15 @@ class Engine:
         flags = self._zs(ws, "flags", torch.int32)
         wl_build = self._zs(ws, "wl_build", torch.int32) if self.dense_worklists else None
         # ---- event level ---------------------------------------------------------------------
-        self._run("graph_sort", lib.dagr_graph_sort, g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ws["key"]),
-                                       _lib.ptr(ws["tmp"]), _lib.ptr(ws["count"]), _lib.ptr(ws["blocksums"]),
-                                       _lib.ptr(ws["start"]), _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                                       _lib.ptr(ws["feat_s"]), _lib.ptr(flags), st)
+        if ring is not None:
+            self._run("graph_sort", lib.dagr_graph_sort_ring, g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ring),
+                      _lib.ptr(ws["key"]), _lib.ptr(ws["tmp"]), _lib.ptr(ws["count"]), _lib.ptr(ws["blocksums"]), _lib.ptr(ws["start"]),
+                      _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(flags), st)
+        else:
+            self._run("graph_sort", lib.dagr_graph_sort, g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ws["key"]),
+                      _lib.ptr(ws["tmp"]), _lib.ptr(ws["count"]), _lib.ptr(ws["blocksums"]),
+                      _lib.ptr(ws["start"]), _lib.ptr(ws["perm"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
+                      _lib.ptr(ws["feat_s"]), _lib.ptr(flags), st)
         use_image = image_feats is not None
         if use_image:
             # adjacency only; conv_block1 runs on [polarity, 16 image samples, x, y] (net.py:117-126)
@@ -575,7 +584,7 @@ class Engine:
         gkey = (id(ws.base), slot, id(pk), B, kto, cellmask.data_ptr())
 
         def run_coarse():
-            if self.use_graphs and self.prof is None and not use_image:
+            if self.use_graphs and self.prof is None and not use_image and ring is None:
                 cached = ws.get("graph")
                 if cached is not None and cached[0] == gkey:
                     cached[1].replay()

@@ -1,0 +1,217 @@
+"""Continuous streaming detection (BASELINE.json configs[4]: one ~1 Mevents/s stream per GPU, 1 ms chunks, 50 ms live window).
+
+What the reference offers for this: `SlidingWindowGraph` with a `min_index` watermark (src/dagr/graph/ev_graph.py:121-136,
+ev_graph.cu:62) that the model never uses, and an asynchronous engine that can do ONE update after its initialisation
+(SURVEY section 0, fact 4).  The contract here is the one a consumer needs: after every chunk the detections equal the
+synchronous forward over the live window (events with t >= t_chunk_end - window), exactly.
+
+How a step works (everything on the device, ONE CUDA graph replay per chunk, no host synchronisation inside):
+
+  pinned stage --H2D--> dagr_stream_push      evicts the window's prefix older than t_cut by moving the ring's head
+                                              (binary search over the time-sorted ring, O(log n), no data movement) and
+                                              appends the chunk behind the tail
+               --> dagr_graph_sort_ring       cell-major counting sort of the live window read through the ring
+               --> k_l1_build / k_l1_conv_b2  event level (launches cover the ring capacity; the live count is device data)
+               --> coarse stack, head, NMS    fixed-shape launches
+               --D2H--> pinned detections
+
+Why the event level is recomputed over the window instead of patched: evicting an event changes the neighbour lists of
+every node it fed (the K cap admits the next candidate of the spiral), i.e. of the window's oldest 10 ms -- and their
+activations feed the next 10 ms.  At 50 k live events the per-voxel kernels take ~0.1 ms for the WHOLE window
+(they are built for 2.4 M events per launch), less than bookkeeping a change set would; the append-only incremental
+path (only new events probed / convolved, `min_idx`) remains available in dagr_b200.asynchronous for the reference's
+own init + update criterion.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class StreamingDetector:
+    """det = StreamingDetector(model, window_us=50_000); det.push(x, y, t, p) -> list with one dict(boxes, scores, labels)."""
+
+    def __init__(self, model, window_us: int = 50_000, max_chunk: int = 8192, capacity: int = 1 << 17, device=None):
+        if model.backbone.use_image:
+            raise NotImplementedError("streaming mode drives the events-only model")
+        self.model, self.eng = model, model.engine
+        self.lib = self.eng.lib
+        self.W, self.H = int(model.width), int(model.height)
+        self.window_us, self.max_chunk = int(window_us), int(max_chunk)
+        cap = 1
+        while cap < capacity:
+            cap <<= 1
+        self.cap = cap
+        dev = torch.device(device) if device is not None else next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("dagr_b200: streaming needs a CUDA device (no CPU fallback)")
+        self.dev = dev
+        self.batch = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.pos = torch.zeros((cap, 3), dtype=torch.int32, device=dev)
+        self.feat = torch.zeros(cap, dtype=torch.float32, device=dev)
+        self.ctl = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.stage_h = torch.zeros(4 + 4 * self.max_chunk, dtype=torch.int32).pin_memory()
+        self.stage_d = torch.zeros(4 + 4 * self.max_chunk, dtype=torch.int32, device=dev)
+        self._stage_np = self.stage_h.numpy()
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graph = None
+        self._res_h = None
+        self._done = None
+        self._warm = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def reset(self):
+        if self._done is not None:
+            self._done.synchronize()
+        self.ctl.zero_()
+
+    def _enqueue(self):
+        """one streaming step on the current stream (eager or under capture)."""
+        m, eng = self.model, self.eng
+        self.stage_d.copy_(self.stage_h, non_blocking=True)
+        _lib.check(self.lib.dagr_stream_push(_lib.ptr(self.ctl), _lib.ptr(self.stage_d), _lib.ptr(self.batch), _lib.ptr(self.pos),
+                                             _lib.ptr(self.feat), self.cap, self.max_chunk, 0, _lib.stream_ptr()), "stream_push")
+        eng.launches += 2
+        dec = eng.forward_events(self.batch, self.pos, self.feat, 1, self.W, self.H, ring=self.ctl)
+        det, ndet = eng.postprocess(dec, m.conf_threshold, m.nms_threshold, self.W, self.H)
+        if self._res_h is None:
+            self._res_h = (torch.empty(det.shape, dtype=det.dtype).pin_memory(), torch.empty(ndet.shape, dtype=ndet.dtype).pin_memory(),
+                           torch.empty(8, dtype=torch.int32).pin_memory())
+        self._res_h[0].copy_(det, non_blocking=True)
+        self._res_h[1].copy_(ndet, non_blocking=True)
+        self._res_h[2].copy_(self.ctl, non_blocking=True)
+
+    def _fill_stage(self, x, y, t, p, t_end):
+        n = int(len(t))
+        if n > self.max_chunk:
+            raise ValueError(f"chunk of {n} events exceeds max_chunk={self.max_chunk}")
+        st = self._stage_np
+        st[0] = n
+        st[1] = int(t_end) - self.window_us
+        if n:
+            ev = st[4:4 + 4 * n].reshape(n, 4)
+            ev[:, 0] = x; ev[:, 1] = y; ev[:, 2] = t; ev[:, 3] = p
+
+    @torch.no_grad()
+    def submit(self, x, y, t, p, t_end=None):
+        """enqueue one chunk (host arrays: pixel x, y, timestamp t in us (int32 range, non-decreasing across pushes),
+        polarity -1/+1).  `t_end` = end of the chunk's time slice (default: its last timestamp); events older than
+        t_end - window_us leave the live window.  Returns immediately; `result()` blocks on the step."""
+        if self._done is not None:
+            self._done.synchronize()                                  # the stage / result buffers of the previous step are free
+        if t_end is None:
+            t_end = int(t[-1]) if len(t) else int(self._stage_np[1]) + self.window_us
+        self._fill_stage(np.asarray(x), np.asarray(y), np.asarray(t), np.asarray(p), t_end)
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_stream(cur)
+            if self.graph is not None:
+                self.graph.replay()
+                self.eng.launches += self._graph_launches
+            else:
+                l0 = self.eng.launches
+                self._enqueue()
+                self._warm += 1
+                if self._warm >= 2:                                   # buffers exist: capture the step once, replay from now on
+                    self._graph_launches = self.eng.launches - l0
+                    self.stream.synchronize()
+                    saved = self.ctl.clone()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        self._enqueue()
+                    self.eng.launches -= self._graph_launches          # capture enqueues nothing
+                    self.ctl.copy_(saved)                              # (the captured step did not run)
+                    self.graph = g
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._done = ev
+
+    def result(self):
+        """detections of the last submitted chunk: [dict(boxes f32[n,4] xyxy px, scores f32[n], labels i64[n])] (host tensors)."""
+        self._done.synchronize()
+        det_h, ndet_h, _ = self._res_h
+        n = int(ndet_h[0])
+        d = det_h[0, :n]
+        return [dict(boxes=d[:, :4].clone(), scores=d[:, 4].clone(), labels=d[:, 5].long())]
+
+    def push(self, x, y, t, p, t_end=None):
+        self.submit(x, y, t, p, t_end)
+        return self.result()
+
+    @property
+    def window_state(self):
+        """(head slot, live events, evicted by the last step, appended by the last step, overflow flag) of the last finished step."""
+        self._done.synchronize()
+        c = self._res_h[2]
+        return dict(head=int(c[0]), live=int(c[1]), evicted=int(c[2]), appended=int(c[3]), overflow=bool(c[4]))
+
+    def live_window(self):
+        """(pos int32[n,3], polarity f32[n]) of the live window in arrival order (host sync; for tests)."""
+        self._done.synchronize()
+        torch.cuda.synchronize(self.dev)
+        head, n = int(self.ctl[0]), int(self.ctl[1])
+        idx = (head + torch.arange(n, device=self.dev)) & (self.cap - 1)
+        return self.pos[idx], self.feat[idx]
+
+
+def synth_stream(rate_ev_s: int, seconds: float, width: int, height: int, seed: int = 99, kind: str = "uniform"):
+    """host arrays (x int16, y int16, t int32 us from 0, p int8) of one continuous synthetic stream."""
+    from .data import synth_sample
+    n = int(rate_ev_s * seconds)
+    window_us = int(seconds * 1e6)
+    x, y, t, p = synth_sample(n, width, height, seed, kind, time_window=window_us, window_us=window_us)
+    return x.numpy(), y.numpy(), t.numpy(), p.numpy()
+
+
+def stream_benchmark(dev, size="l", width=640, height=480, rate_ev_s=1_000_000, chunk_us=1000, window_us=50_000, seconds=2.0,
+                     kind="uniform", model=None):
+    """config 5: per-chunk latency (host submit -> detections on the host) and sustained rate of ONE stream on ONE GPU.
+    Latency mode: a chunk is submitted, its detections are awaited, then the next chunk is submitted (a real-time consumer);
+    the wall clock per chunk is what a 1 ms chunk period has to accommodate."""
+    from .model.dagr import DAGR
+    from .utils.args import default_args
+    if model is None:
+        from tests.helpers import randomize_bn
+        torch.manual_seed(0)
+        model = randomize_bn(DAGR(default_args(size, batch_size=1), height=height, width=width).eval()).to(dev)
+    total_s = seconds + window_us * 1e-6 + 0.02
+    x, y, t, p = synth_stream(rate_ev_s, total_s, width, height, kind=kind)
+    det = StreamingDetector(model, window_us=window_us, max_chunk=max(4096, int(rate_ev_s * chunk_us * 1e-6 * 4)))
+    bounds = np.searchsorted(t, np.arange(0, int(total_s * 1e6) + chunk_us, chunk_us))
+    nchunks = len(bounds) - 1
+    lat, dev_ms, evs = [], [], []
+    warm = int(window_us / chunk_us) + 20                                # fill the live window first (+ graph capture)
+    for k in range(nchunks):
+        a, b = int(bounds[k]), int(bounds[k + 1])
+        t_end = (k + 1) * chunk_us
+        if k >= warm:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(det.stream)
+            det.submit(x[a:b], y[a:b], t[a:b], p[a:b], t_end)
+            e1.record(det.stream)
+            out = det.result()
+            lat.append((time.perf_counter() - t0) * 1e3)
+            dev_ms.append(e0.elapsed_time(e1))
+            evs.append(b - a)
+        else:
+            det.push(x[a:b], y[a:b], t[a:b], p[a:b], t_end)
+    st = det.window_state
+    lat_s, dev_s = sorted(lat), sorted(dev_ms)
+    q = lambda v, f: v[min(len(v) - 1, int(f * len(v)))]
+    busy = sum(lat) * 1e-3
+    return dict(model=f"dagr-{size}", stream_rate_mev_s=rate_ev_s / 1e6, chunk_us=chunk_us, window_us=window_us,
+                stream_seconds=len(lat) * chunk_us * 1e-6, chunks=len(lat), events_per_chunk=float(np.mean(evs)),
+                live_events=st["live"], overflow=st["overflow"],
+                latency_ms=dict(p50=q(lat_s, 0.5), p90=q(lat_s, 0.9), p99=q(lat_s, 0.99), max=lat_s[-1]),
+                device_ms=dict(p50=q(dev_s, 0.5), p99=q(dev_s, 0.99)),
+                sustained_mev_s=sum(evs) / busy / 1e6, realtime=bool(q(lat_s, 0.99) * 1e3 <= chunk_us),
+                realtime_margin=chunk_us / (q(lat_s, 0.5) * 1e3),
+                note="one stream on one GPU; every chunk: H2D of the chunk from pinned memory, eviction by watermark + append into the "
+                     "device ring, full forward over the live window, NMS, D2H of the detections -- one CUDA graph replay; latency = host "
+                     "wall clock from submit() to the detections being readable on the host, chunks submitted back to back "
+                     "(sustained_mev_s = events / busy time: how much faster than the 1 Mevents/s feed the loop runs)")

@@ -91,6 +91,22 @@ int dagr_graph_sort(const dagr_geom_t *g, const int32_t *batch, const int32_t *p
                     int32_t *flags /* i32[1], zero on entry; [0]=1 if a sample is not time-sorted; may be NULL */,
                     void *stream);
 
+/* Streaming form of dagr_graph_sort (BASELINE config 5; the sliding window the reference sketches with min_index,
+ * src/dagr/graph/ev_graph.py:121-136, ev_graph.cu:62).  The live events of one stream sit time-sorted in ring buffers
+ * batch/pos/feat of `capacity` (a power of two) slots; ctl i32[8] on the DEVICE = {head slot, live count, evicted by the last
+ * push, appended by the last push, sticky overflow flag, kept count}.  Event i of the window is slot (head + i) & (capacity-1)
+ * and i is its arrival index for this step.  The launch covers the capacity, so neither call depends on a host-side count:
+ * a whole streaming step can be captured once and replayed as a CUDA graph.  Downstream kernels take N = capacity as the
+ * leading dimension of the ELL / activation arrays.
+ *   dagr_stream_push : stage i32[4 + 4*max_chunk] on the device = {n_new, t_cut, 0, 0, (x, y, t, polarity +-1) * n_new}:
+ *                      evicts the prefix with t < t_cut (binary search, no data movement) and appends the chunk. */
+int dagr_graph_sort_ring(const dagr_geom_t *g, const int32_t *batch, const int32_t *pos, const float *feat,
+                         int64_t capacity, const int32_t *ctl, int32_t *key, int32_t *tmp, int32_t *count,
+                         int32_t *blocksums, int32_t *start, int32_t *perm, int32_t *ti, uint32_t *xyb, float *feat_s,
+                         int32_t *flags, void *stream);
+int dagr_stream_push(int32_t *ctl, const int32_t *stage, int32_t *batch, int32_t *pos, float *feat, int64_t capacity,
+                     int max_chunk, int sample, void *stream);
+
 int dagr_graph_search(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
                       const uint32_t *xyb, int32_t *nbr, uint16_t *off, uint32_t *cellmask,
                       void *stream);

@@ -729,3 +729,41 @@ def test_ingest_window_vs_oracle_and_forward():
     for a, b_ in zip(det_int, det_f):
         assert a["boxes"].shape == b_["boxes"].shape
         assert_close(a["boxes"].cpu(), b_["boxes"].cpu(), what="boxes (ingest vs float batch)")
+
+
+def test_streaming_window_equals_dense_forward_on_live_window():
+    """dagr_b200.streaming (config 5): watermark eviction + append in a device ring, the whole step one CUDA graph replay.
+    After every chunk the detections must equal the synchronous forward over the live window -- checked before the window
+    is full, across >= 3 evictions, and on both the eager (first two) and the replayed steps."""
+    import numpy as np
+    from dagr_b200.data import EventBatch
+    from dagr_b200.streaming import StreamingDetector, synth_stream
+    W, H = 320, 215
+    model, args = make_model("s", H, W, batch_size=1)
+    model.cuda()
+    window_us, chunk_us = 20_000, 2_000
+    x, y, t, p = synth_stream(400_000, 0.06, W, H, seed=5, kind="clustered")
+    det = StreamingDetector(model, window_us=window_us, max_chunk=4096, capacity=1 << 15)
+    bounds = np.searchsorted(t, np.arange(0, 60_000 + chunk_us, chunk_us))
+    checked = 0
+    for k in range(len(bounds) - 1):
+        a, b = int(bounds[k]), int(bounds[k + 1])
+        t_end = (k + 1) * chunk_us
+        out = det.push(x[a:b], y[a:b], t[a:b], p[a:b], t_end)
+        if k in (0, 1, 2, 5, 11, 12, 13, 20, 29):
+            st = det.window_state
+            live = (t >= t_end - window_us) & (t < t_end)
+            assert st["live"] == int(live.sum()) and not st["overflow"], (k, st, int(live.sum()))
+            if k >= 11:
+                assert st["evicted"] > 0
+            pos, feat = det.live_window()
+            assert np.array_equal(pos[:, 2].cpu().numpy(), t[live])
+            n = len(feat)
+            d = EventBatch(x=feat.view(-1, 1).clone(), pos=torch.zeros(n, 3, device="cuda"), batch=torch.zeros(n, dtype=torch.long, device="cuda"),
+                           width=torch.tensor([W]), height=torch.tensor([H]), time_window=torch.tensor([1_000_000]),
+                           pos_denorm=pos.clone(), num_graphs=1, dims=(W, H, 1_000_000))
+            want = model(d)[0][0]
+            assert len(out[0]["boxes"]) == len(want["boxes"]), (k, len(out[0]["boxes"]), len(want["boxes"]))
+            assert torch.equal(out[0]["boxes"], want["boxes"].cpu()) and torch.equal(out[0]["scores"], want["scores"].cpu())
+            checked += 1
+    assert checked == 9 and det.graph is not None
