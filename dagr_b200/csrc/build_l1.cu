@@ -204,14 +204,15 @@ __device__ __forceinline__ int bl_probe_coop(const dagr_geom_t &g, int64_t N, in
     return n;
 }
 
-// work list layout (int32): [0] = number of pushed voxels, [1] = pop cursor of the dense kernel, [2..] = voxel ids
+// work list: wl_hdr[0] = number of voxels beyond this instance's staging capacity (queued in wl_ids when `defer`, otherwise
+// only counted and probed from global memory), wl_hdr[1] = pop cursor of the dense kernel
 template <int CAP, int THREADS>
 __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const int32_t *__restrict__ start, const int2 *__restrict__ ti,
                                          const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
                                          const dagr_l1a_params_t &P, const int do_conv, const int min_idx, const int32_t *__restrict__ flags,
                                          int32_t *__restrict__ nbr, uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask,
                                          float *__restrict__ xa, const int cell, unsigned char *smem_raw, BLTile &T, uint32_t &s_mask,
-                                         int32_t *__restrict__ worklist)
+                                         int32_t *__restrict__ wl_hdr, int32_t *__restrict__ wl_ids, const int defer)
 {
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
@@ -256,11 +257,12 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
     uint32_t *s_occ_c = s_occ_r + BL_NB * TH;                           // [BL_NB][TW] column occupancy bitmasks
     const int total = T.run_off[2] + T.run_len[2];
     const bool staged = total <= CAP;                                   // block-uniform
-    if (!staged && worklist != nullptr) {
+    if (!staged && wl_hdr != nullptr) {
         // too many records for this instance's staging buffer: hand the voxel to the dense kernel (which runs next on
-        // the stream) instead of probing global memory
-        if (threadIdx.x == 0) worklist[2 + atomicAdd(&worklist[0], 1)] = cell;
-        return;
+        // the stream) instead of probing global memory -- or, when the caller did not ask for that, just count it
+        int slot = 0;
+        if (threadIdx.x == 0) slot = atomicAdd(&wl_hdr[0], 1);
+        if (defer) { if (threadIdx.x == 0) wl_ids[slot] = cell; return; }
     }
     const int bbase = b * per * g.CP;
 
@@ -510,13 +512,13 @@ k_l1_build(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, co
            const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
            const __grid_constant__ dagr_l1a_params_t P, const int do_conv, const int min_idx, const int32_t *__restrict__ flags,
            int32_t *__restrict__ nbr, uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask, float *__restrict__ xa,
-           int32_t *__restrict__ worklist)
+           int32_t *__restrict__ wl_hdr, int32_t *__restrict__ wl_ids, const int defer)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BLTile T;
     __shared__ uint32_t s_mask;
     bl_voxel<BL_CAP, BL_THREADS>(g, N, start, ti, xyb, feat_s, tab, P, do_conv, min_idx, flags, nbr, off, cellmask, xa,
-                                 (int)blockIdx.x, smem_raw, T, s_mask, worklist);
+                                 (int)blockIdx.x, smem_raw, T, s_mask, wl_hdr, wl_ids, defer);
 }
 
 // dense voxels: persistent CTAs (one per SM) pop voxel ids from the work list the regular kernel filled
@@ -525,28 +527,28 @@ k_l1_build_dense(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ sta
                  const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s, const float *__restrict__ tab,
                  const __grid_constant__ dagr_l1a_params_t P, const int do_conv, const int min_idx, const int32_t *__restrict__ flags,
                  int32_t *__restrict__ nbr, uint16_t *__restrict__ off, uint32_t *__restrict__ cellmask, float *__restrict__ xa,
-                 int32_t *__restrict__ worklist)
+                 int32_t *__restrict__ wl_hdr, const int32_t *__restrict__ wl_ids)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BLTile T;
     __shared__ uint32_t s_mask;
     __shared__ int s_next;
-    const int count = worklist[0];
+    const int count = wl_hdr[0];
     for (;;) {
         __syncthreads();                                                // everyone is done with the previous voxel
-        if (threadIdx.x == 0) s_next = atomicAdd(&worklist[1], 1);
+        if (threadIdx.x == 0) s_next = atomicAdd(&wl_hdr[1], 1);
         __syncthreads();
         const int i = s_next;
         if (i >= count) break;
         bl_voxel<BL_CAP_BIG, BL_THREADS_BIG>(g, N, start, ti, xyb, feat_s, tab, P, do_conv, min_idx, flags, nbr, off, cellmask, xa,
-                                             worklist[2 + i], smem_raw, T, s_mask, nullptr);
+                                             wl_ids[i], smem_raw, T, s_mask, nullptr, nullptr, 0);
     }
 }
 
 extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const int32_t *ti,
                              const uint32_t *xyb, const float *feat_s, const float *tab,
                              const dagr_l1a_params_t *p_host, const int32_t *flags, int min_idx, int32_t *nbr, uint16_t *off,
-                             uint32_t *cellmask, float *xa, int32_t *worklist, void *stream)
+                             uint32_t *cellmask, float *xa, int32_t *wl_hdr, int32_t *wl_ids, int defer, void *stream)
 {
     DAGR_CHECK_ARG(g, "null argument");
     static const dagr_l1a_params_t zero_params = {};
@@ -560,9 +562,10 @@ extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *sta
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     k_l1_build<<<cells, BL_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab, *p_host,
-                                                                  do_conv, min_idx, flags, nbr, off, cellmask, xa, worklist);
+                                                                  do_conv, min_idx, flags, nbr, off, cellmask, xa, wl_hdr, wl_ids,
+                                                                  (wl_hdr != nullptr && wl_ids != nullptr && defer) ? 1 : 0);
     DAGR_CHECK_LAUNCH();
-    if (worklist != nullptr) {
+    if (wl_hdr != nullptr && wl_ids != nullptr && defer) {
         const size_t smem_big = bl_smem_bytes(g, BL_CAP_BIG, BL_THREADS_BIG);
         static int n_sm = 0;
         if (n_sm == 0) {
@@ -573,7 +576,7 @@ extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *sta
         DAGR_CUDA(cudaFuncSetAttribute(k_l1_build_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
         k_l1_build_dense<<<n_sm, BL_THREADS_BIG, smem_big, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab,
                                                                                     *p_host, do_conv, min_idx, flags, nbr, off,
-                                                                                    cellmask, xa, worklist);
+                                                                                    cellmask, xa, wl_hdr, wl_ids);
         DAGR_CHECK_LAUNCH();
     }
     return DAGR_OK;

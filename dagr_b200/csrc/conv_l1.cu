@@ -474,7 +474,8 @@ struct CB2Shared {
 // staged 8-channel chunks, skip + act + pool1 epilogue); <dagr_l1img_params_t, 3, true> is the image-fusion variant of
 // conv_block1.conv_block1 (1 + 16 + 2 input channels padded to 3 chunks; epilogue = BN + act, rows written back
 // chunk-major for conv_block2, plus the layer's skip branch BN(Linear(x0)) -> skip_out; no pooling).
-// work list layout (int32): [0] = number of queued voxels, [1] = pop cursor of the dense kernel, [2..] = voxel ids
+// work list: wl_hdr[0] = number of voxels beyond this instance's staging capacity (queued in wl_ids when `defer`, otherwise
+// only counted and gathered from global memory / L2), wl_hdr[1] = pop cursor of the dense kernel
 template <class PT, int NCH, bool MODE_A, int CAP, int THREADS>
 __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
              const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
@@ -483,7 +484,8 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
              float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
              float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx,
              float *__restrict__ xa_out, float *__restrict__ skip_out,
-             const int cell, unsigned char *smem_raw, CB2Shared<THREADS> &S, uint32_t &parity, int32_t *__restrict__ worklist)
+             const int cell, unsigned char *smem_raw, CB2Shared<THREADS> &S, uint32_t &parity,
+             int32_t *__restrict__ wl_hdr, int32_t *__restrict__ wl_ids, const int defer)
 {
     CB2Tile &T = S.T;
     uint64_t &s_bar = S.bar;
@@ -531,10 +533,12 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
     __syncthreads();
     const int total = T.run_off[2] + T.run_len[2];
     const bool staged = total <= CAP;                                    // block-uniform
-    if (!staged && worklist != nullptr) {
-        // more rows than this instance can stage: queue the voxel for the dense kernel (next launch on the stream)
-        if (threadIdx.x == 0) worklist[2 + atomicAdd(&worklist[0], 1)] = cell;
-        return;
+    if (!staged && wl_hdr != nullptr) {
+        // more rows than this instance can stage: queue the voxel for the dense kernel (next launch on the stream) -- or,
+        // when the caller did not ask for that, just count it
+        int slot = 0;
+        if (threadIdx.x == 0) slot = atomicAdd(&wl_hdr[0], 1);
+        if (defer) { if (threadIdx.x == 0) wl_ids[slot] = cell; return; }
     }
     const int s1 = T.run_start[1];
     const int s2 = T.run_len[2] > 0 ? T.run_start[2] : 0x7fffffff;
@@ -783,14 +787,15 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
              const __grid_constant__ PT P, const float *__restrict__ skip_pre, const int min_idx,
              float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
              float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx,
-             float *__restrict__ xa_out, float *__restrict__ skip_out, int32_t *__restrict__ worklist)
+             float *__restrict__ xa_out, float *__restrict__ skip_out, int32_t *__restrict__ wl_hdr, int32_t *__restrict__ wl_ids,
+             const int defer)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) CB2Shared<CB2_THREADS> S;
     if (threadIdx.x == 0) mbar_init(&S.bar, 1);                         // made visible by the routine's first __syncthreads
     uint32_t parity = 0;
     cb2_voxel<PT, NCH, MODE_A, CB2_CAP, CB2_THREADS>(g, N, start, xyb, ti, feat_s, xa, nbr, off, P, skip_pre, min_idx, persist, x1, cnt, pxy,
-                                                      tmean, tmax, xg, ldx, xa_out, skip_out, (int)blockIdx.x, smem_raw, S, parity, worklist);
+                                                      tmean, tmax, xg, ldx, xa_out, skip_out, (int)blockIdx.x, smem_raw, S, parity, wl_hdr, wl_ids, defer);
 }
 
 // dense voxels: persistent CTAs (one per SM) pop voxel ids from the work list the regular kernel filled
@@ -802,23 +807,23 @@ k_l1_conv_b2_dense(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ s
                    const __grid_constant__ PT P, const float *__restrict__ skip_pre, const int min_idx,
                    float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
                    float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx,
-                   float *__restrict__ xa_out, float *__restrict__ skip_out, int32_t *__restrict__ worklist)
+                   float *__restrict__ xa_out, float *__restrict__ skip_out, int32_t *__restrict__ wl_hdr, const int32_t *__restrict__ wl_ids)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) CB2Shared<CB2_THREADS_BIG> S;
     __shared__ int s_next;
     if (threadIdx.x == 0) mbar_init(&S.bar, 1);
     uint32_t parity = 0;                                                // the barrier's phase carries over from voxel to voxel
-    const int count = worklist[0];
+    const int count = wl_hdr[0];
     for (;;) {
         __syncthreads();                                                // everyone is done with the previous voxel
-        if (threadIdx.x == 0) s_next = atomicAdd(&worklist[1], 1);
+        if (threadIdx.x == 0) s_next = atomicAdd(&wl_hdr[1], 1);
         __syncthreads();
         const int i = s_next;
         if (i >= count) break;
         cb2_voxel<PT, NCH, MODE_A, CB2_CAP_BIG, CB2_THREADS_BIG>(g, N, start, xyb, ti, feat_s, xa, nbr, off, P, skip_pre, min_idx, persist, x1,
-                                                                  cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, worklist[2 + i],
-                                                                  smem_raw, S, parity, nullptr);
+                                                                  cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, wl_ids[i],
+                                                                  smem_raw, S, parity, nullptr, nullptr, 0);
     }
 }
 
@@ -831,7 +836,7 @@ template <class PT, int NCH, bool MODE_A>
 static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb, const int2 *ti, const float *feat_s,
                       const float *xa, const int32_t *nbr, const uint16_t *off, const PT *p_host, const float *skip_pre, int min_idx,
                       float *persist, float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg, int ldx,
-                      float *xa_out, float *skip_out, int32_t *worklist, cudaStream_t st)
+                      float *xa_out, float *skip_out, int32_t *wl_hdr, int32_t *wl_ids, int defer, cudaStream_t st)
 {
     const int cells = g->B * g->ny1 * g->nx1;
     const size_t smem = cb2_smem_bytes(g, CB2_CAP, CB2_THREADS);
@@ -839,9 +844,10 @@ static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, con
     DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<cells, CB2_THREADS, smem, st>>>(*g, N, start, xyb, ti, feat_s, xa, nbr, off, *p_host, skip_pre, min_idx, persist, x1, cnt, pxy,
-                                           tmean, tmax, xg, ldx, xa_out, skip_out, worklist);
+                                           tmean, tmax, xg, ldx, xa_out, skip_out, wl_hdr, wl_ids,
+                                           (wl_hdr != nullptr && wl_ids != nullptr && defer) ? 1 : 0);
     DAGR_CHECK_LAUNCH();
-    if (worklist != nullptr) {
+    if (wl_hdr != nullptr && wl_ids != nullptr && defer) {
         static int n_sm = 0;
         if (n_sm == 0) {
             int dev = 0;
@@ -852,7 +858,7 @@ static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, con
         auto kd = k_l1_conv_b2_dense<PT, NCH, MODE_A>;
         DAGR_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
         kd<<<n_sm, CB2_THREADS_BIG, smem_big, st>>>(*g, N, start, xyb, ti, feat_s, xa, nbr, off, *p_host, skip_pre, min_idx, persist, x1,
-                                                    cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, worklist);
+                                                    cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, wl_hdr, wl_ids);
         DAGR_CHECK_LAUNCH();
     }
     return DAGR_OK;
@@ -862,26 +868,27 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
                                          const int32_t *ti, const float *feat_s, const float *xa, const int32_t *nbr,
                                          const uint16_t *off, const float *tab, const dagr_l1b_params_t *p_host,
                                          const float *skip_pre, int min_idx, float *persist, float *x1, int32_t *cnt,
-                                         int32_t *pxy, float *tmean, float *tmax, float *xg, int ldx, int32_t *worklist, void *stream)
+                                         int32_t *pxy, float *tmean, float *tmax, float *xg, int ldx, int32_t *wl_hdr, int32_t *wl_ids,
+                                         int defer, void *stream)
 {
     (void)tab;
     DAGR_CHECK_ARG(g && p_host, "null argument");
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
     return cb2_launch<dagr_l1b_params_t, 2, false>(g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, p_host, skip_pre, min_idx,
-                                                   persist, x1, cnt, pxy, tmean, tmax, xg, ldx, nullptr, nullptr, worklist,
+                                                   persist, x1, cnt, pxy, tmean, tmax, xg, ldx, nullptr, nullptr, wl_hdr, wl_ids, defer,
                                                    (cudaStream_t)stream);
 }
 
 // image fusion: conv_block1.conv_block1 on the 19-channel rows x0 (chunk-major [3][N][8], chunks swizzled like xa)
 extern "C" int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const float *x0, const int32_t *nbr,
                                     const uint16_t *off, const dagr_l1img_params_t *p_host, float *xa, float *skipv,
-                                    int32_t *worklist, void *stream)
+                                    int32_t *wl_hdr, int32_t *wl_ids, int defer, void *stream)
 {
     DAGR_CHECK_ARG(g && p_host, "null argument");
     if (N <= 0) return DAGR_OK;
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
     return cb2_launch<dagr_l1img_params_t, 3, true>(g, N, start, nullptr, nullptr, nullptr, x0, nbr, off, p_host, nullptr, 0, nullptr,
-                                                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, xa, skipv, worklist,
+                                                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, xa, skipv, wl_hdr, wl_ids, defer,
                                                     (cudaStream_t)stream);
 }
 

@@ -102,8 +102,11 @@ class Engine:
         self.voxel_conv_b = True             # conv_b + pool1 as one CTA per voxel with TMA-staged rows (False: v1)
         self.use_graphs = True               # replay the fixed-shape coarse stack as a CUDA graph
         self.fused_build = True              # probe + conv_a in one shared-memory-tiled kernel (False: v1 split kernels)
-        self.dense_worklists = True          # voxels beyond the per-voxel kernels' staging capacity go to the persistent dense
-                                             # kernels (False: global-memory fallback inside the per-voxel kernels, for A/B tests)
+        # voxels beyond the per-voxel kernels' staging capacity (moving edges): "auto" = the kernels always COUNT them; once a
+        # forward has seen some, the following forwards queue them for the persistent dense kernels (two more launches, ~45 us
+        # even when empty, which is why uniform streams do not pay for them); True / False force the behaviour (tests, A/B)
+        self.dense_worklists = "auto"
+        self._dense = {}                     # workspace id -> dict(defer=[build, conv_a, conv_b], host=pinned i32[8], event, quiet)
         self.last = {}
         self.launches = 0                    # kernels of libdagr_b200.so enqueued so far
         self.prof = None                     # dict name -> [(start_evt, end_evt)] when per-op timing is on
@@ -281,8 +284,9 @@ class Engine:
                 take(f"ptmax{lv}", cells * 4)
                 take(f"pcnt{lv}", cells * 4)
                 take(f"pmask{lv}", cells * 4)
-            for wl in ("wl_build", "wl_conv_a", "wl_conv_b"):     # dense-voxel work lists: [count, cursor, voxel ids ...]
-                take(wl, (geom.cells1 + 2) * 4)
+            take("wl_hdr", 32)                                   # dense-voxel work lists: (count, cursor) x {build, conv_a, conv_b}
+            for wl in ("wl_build", "wl_conv_a", "wl_conv_b"):     # ... and the queued voxel ids
+                take(wl, geom.cells1 * 4)
             take("err", 4)
             take("flags", 16)
             ws["zero_buf"] = torch.zeros(off, dtype=torch.uint8, device=dev)
@@ -324,6 +328,39 @@ class Engine:
     def result_stream(self):
         """context manager: the stream on which the last forward's results are produced (current stream if serial)."""
         return torch.cuda.stream(self._cstream if (self.overlap and self._cstream is not None) else torch.cuda.current_stream())
+
+    def _dense_policy(self, ws, wl_hdr, fixed: bool):
+        """which of (build, conv_a_image, conv_b) hand their over-capacity voxels to the dense kernels in this forward."""
+        if self.dense_worklists is True:
+            return [1, 1, 1]
+        if self.dense_worklists is False or fixed:
+            # streaming (captured graph, one sample, <= 100 k live events): the launch list is fixed at capture time and a
+            # 50 ms window of one stream stays far below the staging capacities; over-capacity voxels still work (L2 gathers)
+            return [0, 0, 0]
+        st = self._dense.get(id(ws.base))
+        if st is None:
+            st = dict(defer=[0, 0, 0], host=torch.zeros(8, dtype=torch.int32).pin_memory(), event=None, quiet=[0, 0, 0])
+            self._dense[id(ws.base)] = st
+        if st["event"] is not None and st["event"].query():            # counts of an earlier forward have arrived (no waiting)
+            h = st["host"]
+            for k in range(3):
+                if int(h[2 * k]) > 0:
+                    st["defer"][k], st["quiet"][k] = 1, 0
+                elif st["defer"][k]:
+                    st["quiet"][k] += 1
+                    if st["quiet"][k] >= 16:                            # the stream calmed down: drop the two extra launches
+                        st["defer"][k] = 0
+            st["event"] = None
+        return list(st["defer"])
+
+    def _dense_report(self, ws, wl_hdr):
+        st = self._dense.get(id(ws.base))
+        if st is None or st["event"] is not None:
+            return
+        st["host"].copy_(wl_hdr[:8], non_blocking=True)                 # 32 bytes, no synchronisation; read by a later forward
+        ev = torch.cuda.Event()
+        ev.record()
+        st["event"] = ev
 
     def _zs(self, ws, name, dtype):
         off, nbytes = ws["zero_slices"][name]
@@ -460,7 +497,8 @@ class Engine:
             cellmask, persist, min_idx = stream_state.cellmask, stream_state.voxmax, int(n_old)
         poolmax = self._zs(ws, "poolmax", torch.int32)
         flags = self._zs(ws, "flags", torch.int32)
-        wl_build = self._zs(ws, "wl_build", torch.int32) if self.dense_worklists else None
+        wl_hdr = self._zs(ws, "wl_hdr", torch.int32)
+        defer = self._dense_policy(ws, wl_hdr, ring is not None or stream_state is not None)
         # ---- event level ---------------------------------------------------------------------
         if ring is not None:
             self._run("graph_sort", lib.dagr_graph_sort_ring, g, _lib.ptr(batch_i32), _lib.ptr(pos_i32), _lib.ptr(feat), N, _lib.ptr(ring),
@@ -476,21 +514,23 @@ class Engine:
             # adjacency only; conv_block1 runs on [polarity, 16 image samples, x, y] (net.py:117-126)
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), None, _lib.ptr(flags), 0, _lib.ptr(nbr), _lib.ptr(off),
-                      _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_build), st)
+                      _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_hdr), _lib.ptr(self._zs(ws, "wl_build", torch.int32)), defer[0], st)
             f0 = image_feats[0]
             x0 = self._buf(ws, "x0img", (3 * max(N, 1) * 8,), torch.float32, dev)
             skipv = self._buf(ws, "skipv", (max(N, 1), 16), torch.float32, dev)
             self._run("l1_x0_image", lib.dagr_l1_x0_image, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(f0),
                       int(f0.shape[2]), int(f0.shape[3]), _lib.ptr(x0), st)
             self._run("l1_conv_a_image", lib.dagr_l1_conv_a_image, g, N, _lib.ptr(ws["start"]), _lib.ptr(x0), _lib.ptr(nbr), _lib.ptr(off),
-                      C.byref(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), _lib.ptr(self._zs(ws, "wl_conv_a", torch.int32)), st)
+                      C.byref(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), _lib.ptr(wl_hdr[2:]),
+                      _lib.ptr(self._zs(ws, "wl_conv_a", torch.int32)), defer[1], st)
         elif self.fused_build or stream_state is not None:
             if min_idx > 0:
                 self._run("xa_gather", lib.dagr_xa_permute, N, _lib.ptr(ws["perm"]), min_idx, _lib.ptr(ws["xa"]),
                           _lib.ptr(stream_state.xa_arr), 0, st)
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), C.byref(pk["l1a"]), _lib.ptr(flags), min_idx, _lib.ptr(nbr),
-                      _lib.ptr(off), _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_build), st)
+                      _lib.ptr(off), _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_hdr), _lib.ptr(self._zs(ws, "wl_build", torch.int32)),
+                      defer[0], st)
             if stream_state is not None:
                 self._run("xa_scatter", lib.dagr_xa_permute, N, _lib.ptr(ws["perm"]), min_idx, _lib.ptr(ws["xa"]),
                           _lib.ptr(stream_state.xa_arr), 1, st)
@@ -512,7 +552,8 @@ class Engine:
                       _lib.ptr(ws["ti"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]), _lib.ptr(nbr), _lib.ptr(off),
                       _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(skipv) if use_image else None, min_idx, _lib.ptr(persist),
                       _lib.ptr(x1), _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean), _lib.ptr(g1.tmax), _lib.ptr(g1.x), c1,
-                      _lib.ptr(self._zs(ws, "wl_conv_b", torch.int32)) if self.dense_worklists else None, st)
+                      _lib.ptr(wl_hdr[4:]), _lib.ptr(self._zs(ws, "wl_conv_b", torch.int32)), defer[2], st)
+            self._dense_report(ws, wl_hdr)
             if use_image:                                     # sampling_skip before pool1 (net.py:128-131)
                 f1 = image_feats[1]
                 self._run("voxel_sample_max", lib.dagr_voxel_sample_max, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(f1),

@@ -124,10 +124,12 @@ int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const i
                   int min_idx /* incremental mode: only events with arrival idx >= min_idx are processed and cellmask is
                                  OR-ed into its previous content; 0 = everything */,
                   int32_t *nbr, uint16_t *off, uint32_t *cellmask, float *xa,
-                  int32_t *worklist /* i32[2 + cells], first two words ZERO on entry, or NULL.  Voxels whose 3x3 neighbourhood
-                                       exceeds the regular kernel's staging capacity (2048 records; moving edges) are queued
-                                       here and processed by a second, persistent launch with a 12288-record buffer; with NULL
-                                       (or beyond 12288) they probe global memory instead */,
+                  int32_t *wl_hdr /* i32[2] ZERO on entry, or NULL: [0] counts the voxels whose 3x3 neighbourhood exceeds the
+                                     per-voxel kernel's staging capacity (2048 records; moving edges), [1] is the dense kernel's cursor */,
+                  int32_t *wl_ids /* i32[cells] or NULL: ids of those voxels when `defer` */,
+                  int defer /* 1: such voxels are queued and processed by a second, persistent launch with a 12288-record staging
+                               buffer; 0: they are only counted and probe global memory (slow, exact) -- a caller can watch
+                               wl_hdr[0] and switch `defer` on for streams that have dense voxels */,
                   void *stream);
 
 /* streaming (a13): node rows live in arrival order between steps; gather (scatter=0: rows of nodes < n_old into the
@@ -155,7 +157,8 @@ typedef struct {
 int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const float *x0, const int32_t *nbr,
                          const uint16_t *off, const dagr_l1img_params_t *p_host /* passed by value to the kernel (26 KB) */,
                          float *xa, float *skipv,
-                         int32_t *worklist /* i32[2 + cells] zeroed, or NULL: see dagr_l1_conv_b_pool_voxel */, void *stream);
+                         int32_t *wl_hdr, int32_t *wl_ids, int defer /* dense-voxel work list, see dagr_l1_conv_b_pool_voxel */,
+                         void *stream);
 
 /* per-voxel channel max of image features sampled at the voxel's events (sampling_skip before pool1,
  * net.py:128-131): xg[cell*ldx + c0 + c], c < C, empty voxels -> 0 */
@@ -222,10 +225,11 @@ int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const int32_t *st
                               float *persist /* f32[cells,16] or NULL: running per-voxel max across streaming steps */,
                               float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg,
                               int ldx /* row stride of xg (>= 16) */,
-                              int32_t *worklist /* i32[2 + cells], first two words ZERO on entry, or NULL.  Voxels whose 3x3
-                                                   neighbourhood holds more than 1344 rows are queued here by the per-voxel launch and
-                                                   processed by a second, persistent launch that stages up to 6144 rows (196 KB of
-                                                   shared memory per SM); with NULL (or beyond 6144) rows are gathered from L2 */,
+                              int32_t *wl_hdr /* i32[2] ZERO on entry, or NULL: [0] counts the voxels whose 3x3 neighbourhood holds more
+                                                 than 1344 rows, [1] is the dense kernel's cursor */,
+                              int32_t *wl_ids /* i32[cells] or NULL */,
+                              int defer /* 1: those voxels are queued and processed by a second, persistent launch that stages up to
+                                           6144 rows (196 KB of shared memory per SM); 0: counted only, rows gathered from L2 */,
                               void *stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -357,23 +357,31 @@ def test_cuda_path_equals_the_references_own_forward(name):
 # per-voxel kernels), multi-record pixels; the clustered stream adds voxels beyond the staging capacities
 # (BL_CAP / CB2_CAP -> global-memory fallbacks) and low-degree noise events.
 FULL_DENSITY_CASES = [
-    (1, "uniform", 2042),                 # one sample of the bench batch (bench.py seed 42 + 1000 * 2)
-    (1, "clustered", 2042),
-    (2, "uniform", 2052),
+    # B, stream, seed, Engine.dense_worklists
+    (1, "uniform", 2042, "auto"),         # one sample of the bench batch (bench.py seed 42 + 1000 * 2)
+    (1, "clustered", 2042, False),        # over-capacity voxels: global-memory fallback inside the per-voxel kernels
+    (1, "clustered", 2042, True),         # ... queued for the persistent dense kernels
+    (2, "uniform", 2052, "auto"),
 ]
 
 
-@pytest.mark.parametrize("B,kind,seed", FULL_DENSITY_CASES)
-def test_full_density_forward_parity_vs_oracle(B, kind, seed):
+@pytest.mark.parametrize("B,kind,seed,dense", FULL_DENSITY_CASES)
+def test_full_density_forward_parity_vs_oracle(B, kind, seed, dense):
     W, H, n = 640, 480, 300000
     model, args = make_model("s", H, W, batch_size=B)
     model.cuda()
+    model.engine.dense_worklists = dense
     raw, data = make_inputs(B, n, W, H, seed=seed, kind=kind)
     _check_forward(model, args, data, B, H, W)
     N = model.engine.last["N"]
     deg = model.engine.last["ws"]["nbr"][15 * N:16 * N].float()
     if kind == "uniform":
         assert float(deg.mean()) > 13.0                       # the K cap (15 neighbours + self loop) is hit almost everywhere
+    else:
+        hdr = model.engine._zs(model.engine.last["ws"], "wl_hdr", torch.int32).cpu()
+        assert int(hdr[0]) > 100 and int(hdr[4]) > 100        # this stream really has voxels beyond both staging capacities
+    if dense == "auto" and kind == "uniform":
+        assert model.engine._dense_policy(model.engine.last["ws"], None, False) == [0, 0, 0]
 
 
 def test_last_event_at_t_equals_T_quirk_h3a():

@@ -1,47 +1,37 @@
-#!/usr/bin/env python
-"""per-op timing of incremental steps (config-5 shape): 1 stream, 50 ms history, 1 ms chunks."""
-import sys, time
-from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT))
+"""per-op device time of ONE streaming step (config 5: dagr-l, 640x480, 1 ms chunks of a 1 Mevents/s stream, 50 ms window):
+the step is run eagerly with CUDA events around every C-ABI call (the production path replays it as one CUDA graph)."""
+import json
+import sys
+
+import numpy as np
 import torch
-from dagr_b200.asynchronous import AsyncDAGR
-from dagr_b200.data import EventBatch, format_data, synth_batch
+
+sys.path.insert(0, ".")
 from dagr_b200.model.dagr import DAGR
+from dagr_b200.streaming import StreamingDetector, synth_stream
 from dagr_b200.utils.args import default_args
 from tests.helpers import randomize_bn
 
+W, H = 640, 480
 size = sys.argv[1] if len(sys.argv) > 1 else "l"
-W, H, T = 640, 480, 1_000_000
 torch.manual_seed(0)
-m = randomize_bn(DAGR(default_args(size, batch_size=1), height=H, width=W).eval()).cuda()
-d = format_data(synth_batch(1, 100_000, W, H, seed=99, kind="uniform", window_us=100_000).cuda())
-t_us = (d.pos[:, 2].double() * T).round(); t0 = float(t_us.min())
-eng = AsyncDAGR(m)
-def chunk(lo, hi):
-    c = (t_us >= t0 + lo) & (t_us < t0 + hi)
-    return EventBatch(x=d.x[c], pos=d.pos[c], batch=d.batch[c], width=d.width, height=d.height, time_window=d.time_window, num_graphs=1)
-eng.step(chunk(0, 50_000))
-for k in range(6):
-    eng.step(chunk(50_000 + 1000 * k, 51_000 + 1000 * k))
+model = randomize_bn(DAGR(default_args(size, batch_size=1), height=H, width=W).eval()).cuda()
+x, y, t, p = synth_stream(1_000_000, 0.2, W, H)
+det = StreamingDetector(model, window_us=50_000, max_chunk=4096)
+bounds = np.searchsorted(t, np.arange(0, 200_001, 1000))
+for k in range(80):
+    a, b = int(bounds[k]), int(bounds[k + 1])
+    det.push(x[a:b], y[a:b], t[a:b], p[a:b], (k + 1) * 1000)
 torch.cuda.synchronize()
-# host time vs device time of 10 steps
-chs = [chunk(56_000 + 1000 * k, 57_000 + 1000 * k) for k in range(10)]
-torch.cuda.synchronize(); t1 = time.perf_counter()
-for c in chs: eng.step(c)
-torch.cuda.synchronize(); t2 = time.perf_counter()
-print("wall per step (ms):", (t2 - t1) / 10 * 1e3)
-chs = [chunk(66_000 + 1000 * k, 67_000 + 1000 * k) for k in range(10)]
-t1 = time.perf_counter()
-for c in chs: eng.step_decoded(c, batch_size=1)
-t_host = time.perf_counter() - t1
-torch.cuda.synchronize(); t2 = time.perf_counter()
-print("host enqueue per step_decoded (ms):", t_host / 10 * 1e3, " incl. drain:", (t2 - t1) / 10 * 1e3)
-m.engine.prof = {}
-for k in range(5): eng.step(chunk(76_000 + 1000 * k, 77_000 + 1000 * k))
+eng = model.engine
+eng.prof = {}
+for k in range(80, 110):
+    a, b = int(bounds[k]), int(bounds[k + 1])
+    det._fill_stage(x[a:b], y[a:b], t[a:b], p[a:b], (k + 1) * 1000)
+    det._enqueue()
 torch.cuda.synchronize()
-ps = m.engine.prof_summary(); m.engine.prof = None
-tot = sum(v["ms"] * v["calls"] / 5 for v in ps.values())
-print("sum of per-op device ms per step (eager, with events):", tot)
-for k, v in sorted(ps.items(), key=lambda kv: -kv[1]["ms"] * kv[1]["calls"])[:14]:
-    print(f"  {k:28s} {v['ms']:.4f} ms x {v['calls'] / 5:.0f}")
+prof = eng.prof_summary()
+eng.prof = None
+rows = sorted(((v["ms"] * v["calls"] / 30, k, v["calls"] // 30, v["ms"]) for k, v in prof.items()), reverse=True)
+print(json.dumps(dict(model=f"dagr-{size}", total_ms_per_step=sum(r[0] for r in rows),
+                      per_op=[dict(op=k, calls_per_step=c, ms_each=round(m, 4), ms_per_step=round(tot, 4)) for tot, k, c, m in rows])))
