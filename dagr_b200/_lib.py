@@ -42,6 +42,15 @@ class Grid(C.Structure):
                 ("posxr", p), ("posyr", p)]
 
 
+class EventWs(C.Structure):
+    _fields_ = [(k, i64) for k in ("key", "tmp", "count", "blocksums", "start", "perm", "ti", "xyb", "feat_s", "nbr", "off", "cellmask",
+                                   "xa", "wl_hdr", "wl_ids", "x1")]
+
+
+class PoolWs(C.Structure):
+    _fields_ = [(k, i64) for k in ("acc", "possum", "ptmax", "pcnt", "pmask")]
+
+
 class L1AParams(C.Structure):
     _fields_ = [("w", f32 * (KU * 3 * 16)), ("root", f32 * (3 * 16)),
                 ("scale", f32 * 16), ("shift", f32 * 16), ("relu", i32)]
@@ -62,6 +71,9 @@ _SIGS = {
     "dagr_abi_version": (C.c_int, []),
     "dagr_last_error": (C.c_char_p, []),
     "dagr_scan_blocks": (i64, [i64]),
+    "dagr_check_config": (C.c_int, [C.POINTER(Geom), i64, C.c_int, C.c_int, C.c_char_p]),
+    "dagr_event_workspace_bytes": (C.c_int, [C.POINTER(Geom), i64, C.POINTER(EventWs)]),
+    "dagr_pool_workspace_bytes": (C.c_int, [i64, C.c_int, C.POINTER(PoolWs)]),
     "dagr_downsample_events": (C.c_int, [p, p, p, i64, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p, p, p, p, p, p, p]),
     "dagr_compact_events": (C.c_int, [p, i64, p, p, p, p, C.c_int, C.c_int, p, p, p, p, p, p, p, p, p]),
     "dagr_ingest_events": (C.c_int, [p, p, p, p, i64, C.c_int, C.c_int, C.c_int, C.c_int, i64, C.c_int, p, p, p, p, p, p, p, p, p]),
@@ -81,14 +93,15 @@ _SIGS = {
     "dagr_l1_conv_b_pool_voxel": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, p, p, p, p, C.POINTER(L1BParams), p, C.c_int, p, p, p, p, p, p, p, C.c_int, p, p, C.c_int, p]),
     "dagr_pool1_finalize": (C.c_int, [C.POINTER(Geom), i64, p, p, p, p, C.c_int, p, p, p, p, p, p]),
     "dagr_grid_cat_pos": (C.c_int, [C.POINTER(Grid), p, p, p, C.c_int, p, p]),
-    "dagr_grid_conv": (C.c_int, [C.POINTER(Grid), p, p, p, p, C.c_int, C.c_int, p, p, p, p, p, p, C.c_int, f32, f32, p, p]),
+    "dagr_grid_conv": (C.c_int, [C.POINTER(Grid), p, p, p, p, C.c_int, C.c_int, C.c_int, p, p, p, p, p, p, C.c_int, f32, f32, p, p]),
     "dagr_grid_linear_bn": (C.c_int, [i64, p, p, C.c_int, C.c_int, p, p, p, p, p]),
     "dagr_grid_pool": (C.c_int, [C.POINTER(Grid), C.POINTER(Grid), p, p, p, p, p, p, p, p, C.c_int, C.c_int,
                                  p, p, p, p, p, p, p, p]),
     "dagr_grid_pool_finalize": (C.c_int, [C.POINTER(Grid), C.c_int, C.c_int, p, p, p, p, p, p, p, p, p, p]),
     "dagr_grid_temporal_filter": (C.c_int, [C.POINTER(Grid), p, p, p, p]),
-    "dagr_grid_to_dense": (C.c_int, [C.POINTER(Grid), p, p, C.c_int, p, p, p]),
+    "dagr_grid_to_dense": (C.c_int, [C.POINTER(Grid), p, p, C.c_int, C.c_int, p, p, p]),
     "dagr_head_decode": (C.c_int, [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
+    "dagr_head_finish": (C.c_int, [C.POINTER(Grid), p, p, C.c_int, p, C.c_int, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
     "dagr_postprocess_nms": (C.c_int, [p, C.c_int, C.c_int, C.c_int, f32, f32, C.c_int, C.c_int, C.c_int, p, p, p]),
     "dagr_sample_features": (C.c_int, [p, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p, i64, C.c_int, C.c_int, p,
                                        C.c_int, C.c_int, p]),
@@ -120,7 +133,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dagr_abi_version() != 1:
+    if lib.dagr_abi_version() != 2:
         raise RuntimeError("dagr_b200: ABI version mismatch between python host and libdagr_b200.so")
     _lib = lib
     return lib

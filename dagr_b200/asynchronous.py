@@ -37,10 +37,10 @@ class StreamState:
         self._geom_id = None
 
     def ensure(self, geom, N, dev):
-        if self._geom_id != id(geom):
+        if self._geom_id != (geom.W, geom.H, geom.B, geom.r):
             self.voxmax = torch.full((geom.cells1, 16), float("-inf"), dtype=torch.float32, device=dev)
             self.cellmask = torch.zeros(geom.cells1, dtype=torch.int32, device=dev)
-            self._geom_id = id(geom)
+            self._geom_id = (geom.W, geom.H, geom.B, geom.r)
             self.cap = 0
         if N > self.cap:
             cap = max(int(N * 1.5), 4096)

@@ -131,7 +131,7 @@ extern "C" int dagr_grid_cat_pos(const dagr_grid_t *gr, const int32_t *cnt, cons
 
 __global__ void __launch_bounds__(GC_WARPS * 32)
 k_grid_conv(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t *__restrict__ pxy,
-            const uint32_t *__restrict__ mask, const float *__restrict__ xin, int Cin, int Cout,
+            const uint32_t *__restrict__ mask, const float *__restrict__ xin, int ldin, int Cin, int Cout,
             const float *__restrict__ weight, const float *__restrict__ rootT, const float *__restrict__ bias,
             const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ skip,
             int relu, float den_x, float den_y, float *__restrict__ out)
@@ -167,7 +167,7 @@ k_grid_conv(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t
         const float ay = __fadd_rn(__fdiv_rn((float)dy, den_y), 0.5f);
         float w[4]; int slot[4];
         spline_basis2(ax, ay, 5, w, slot);
-        const float *xs = xin + (int64_t)src * Cin;
+        const float *xs = xin + (int64_t)src * ldin;
         for (int ci = lane; ci < Cin; ci += 32) {
             const float v = xs[ci];
 #pragma unroll
@@ -177,7 +177,7 @@ k_grid_conv(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t
         for (int s = 0; s < 4; s++) if (w[s] != 0.f) used |= 1u << slot[s];
     }
     __syncwarp();
-    const float *xd = xin + (int64_t)cell * Cin;
+    const float *xd = xin + (int64_t)cell * ldin;
     for (int o = lane; o < Cout; o += 32) {
         float acc = 0.f;
         uint32_t u = used;
@@ -211,7 +211,7 @@ k_grid_conv(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t
 template <int CPB>
 __global__ void __launch_bounds__(SK_WARPS * 32)
 k_grid_conv_sk(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int32_t *__restrict__ pxy,
-               const uint32_t *__restrict__ mask, const float *__restrict__ xin, int Cin, int Cout,
+               const uint32_t *__restrict__ mask, const float *__restrict__ xin, int ldin, int Cin, int Cout,
                const float *__restrict__ weight, const float *__restrict__ rootT, const float *__restrict__ bias,
                const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ skip,
                int relu, float den_x, float den_y, float *__restrict__ out)
@@ -272,12 +272,12 @@ table_done:
         const int j = i / Cin, c = i % Cin;
         const int cell = cell0 + j;
         if (cell >= cells || cnt[cell] <= 0) continue;
-        A[((size_t)25 * Cin + c) * CPB + j] = xin[(int64_t)cell * Cin + c];          // root "slot"
+        A[((size_t)25 * Cin + c) * CPB + j] = xin[(int64_t)cell * ldin + c];          // root "slot"
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int src = s_src[j][e];
             if (src < 0) continue;
-            const float v = xin[(int64_t)src * Cin + c];
+            const float v = xin[(int64_t)src * ldin + c];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 float *a = A + ((size_t)s_slot[j][e][q] * Cin + c) * CPB + j;
@@ -360,7 +360,7 @@ table_done:
 
 template <int CPB>
 static int launch_grid_conv_sk(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const uint32_t *mask,
-                               const float *xin, int Cin, int Cout, const float *weight, const float *rootT, const float *bias,
+                               const float *xin, int ldin, int Cin, int Cout, const float *weight, const float *rootT, const float *bias,
                                const float *scale, const float *shift, const float *skip, int relu, float den_x, float den_y,
                                float *out, cudaStream_t st)
 {
@@ -370,35 +370,36 @@ static int launch_grid_conv_sk(const dagr_grid_t *gr, const int32_t *cnt, const 
     if (smem > 200 * 1024) return -1;
     cudaError_t e = cudaFuncSetAttribute(k_grid_conv_sk<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -2;
-    k_grid_conv_sk<CPB><<<dagr_div_up(cells, CPB), SK_WARPS * 32, smem, st>>>(*gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias,
+    k_grid_conv_sk<CPB><<<dagr_div_up(cells, CPB), SK_WARPS * 32, smem, st>>>(*gr, cnt, pxy, mask, xin, ldin, Cin, Cout, weight, rootT, bias,
                                                                             scale, shift, skip, relu, den_x, den_y, out);
     return 0;
 }
 
 extern "C" int dagr_grid_conv(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const uint32_t *mask,
-                              const float *xin, int Cin, int Cout, const float *weight, const float *rootT,
+                              const float *xin, int ldin, int Cin, int Cout, const float *weight, const float *rootT,
                               const float *bias, const float *scale, const float *shift, const float *skip, int relu,
                               float den_x, float den_y, float *out, void *stream)
 {
-    DAGR_CHECK_ARG(gr && Cin > 0 && Cout > 0, "bad channels");
+    DAGR_CHECK_ARG(gr && Cin > 0 && Cout > 0 && (ldin == 0 || ldin >= Cin), "bad channels");
+    if (ldin == 0) ldin = Cin;
     const int cells = gr->B * gr->ny * gr->nx;
     cudaStream_t st = (cudaStream_t)stream;
     // voxels per CTA: enough CTAs to fill 148 SMs, as much weight reuse as shared memory allows
     int rc = -1;
     const size_t per_cell = ((size_t)SK_SLOTS * Cin + (Cout <= 64 ? 0 : (size_t)SK_WARPS * Cout)) * sizeof(float);
     if (cells >= 148 * 16 * 2 && per_cell * 16 <= 110 * 1024)
-        rc = launch_grid_conv_sk<16>(gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
+        rc = launch_grid_conv_sk<16>(gr, cnt, pxy, mask, xin, ldin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
     if (rc != 0 && cells >= 148 * 4 && per_cell * 4 <= 160 * 1024)
-        rc = launch_grid_conv_sk<4>(gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
+        rc = launch_grid_conv_sk<4>(gr, cnt, pxy, mask, xin, ldin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
     if (rc != 0)
-        rc = launch_grid_conv_sk<1>(gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
+        rc = launch_grid_conv_sk<1>(gr, cnt, pxy, mask, xin, ldin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out, st);
     if (rc != 0) {
         // very wide layers: v1 kernel (one warp per voxel)
         const size_t smem = (size_t)GC_WARPS * GC_SLOTS * Cin * sizeof(float);
         DAGR_CHECK_ARG(smem <= 200 * 1024, "Cin too large for the grid conv kernels");
         DAGR_CUDA(cudaFuncSetAttribute(k_grid_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_grid_conv<<<dagr_div_up(cells, GC_WARPS), GC_WARPS * 32, smem, st>>>(
-            *gr, cnt, pxy, mask, xin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out);
+            *gr, cnt, pxy, mask, xin, ldin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out);
     }
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
@@ -407,29 +408,58 @@ extern "C" int dagr_grid_conv(const dagr_grid_t *gr, const int32_t *cnt, const i
 // ------------------------------------------------------------------------------------------------
 // Linear (no bias) + eval BN on valid voxels: the skip branch of ConvBlockWithSkip
 // ------------------------------------------------------------------------------------------------
-__global__ void k_grid_linear_bn(int64_t cells, const int32_t *__restrict__ cnt, const float *__restrict__ xin, int Cin,
-                                 int Cout, const float *__restrict__ wT, const float *__restrict__ scale,
-                                 const float *__restrict__ shift, float *__restrict__ out)
+// One CTA per LB_CELLS voxels: their input rows sit in shared memory, thread (o, half) owns output channel o of four
+// voxels, so every weight is loaded once per four FMAs and the loads of eight rows are in flight before the FMAs (the
+// one-warp-per-voxel form this replaces was a chain of Cin dependent L2 round trips: 22 us for 2240 x 130 x 128).
+#define LB_CELLS 8
+__global__ void __launch_bounds__(256)
+k_grid_linear_bn(int64_t cells, const int32_t *__restrict__ cnt, const float *__restrict__ xin, int Cin,
+                 int Cout, const float *__restrict__ wT, const float *__restrict__ scale,
+                 const float *__restrict__ shift, float *__restrict__ out)
 {
-    const int64_t cell = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (cell >= cells) return;
-    const bool valid = cnt[cell] > 0;
-    const float *xd = xin + cell * Cin;
-    for (int o = lane; o < Cout; o += 32) {
-        float acc = 0.f;
-        if (valid) {
-            for (int ci = 0; ci < Cin; ci++) acc = fmaf(xd[ci], __ldg(wT + (int64_t)ci * Cout + o), acc);
-            if (scale) acc = fmaf(acc, scale[o], shift[o]);
+    extern __shared__ float s_x[];                                       // [LB_CELLS][Cin]
+    __shared__ int s_valid[LB_CELLS];
+    const int64_t cell0 = (int64_t)blockIdx.x * LB_CELLS;
+    for (int i = threadIdx.x; i < LB_CELLS * Cin; i += blockDim.x) {
+        const int64_t cell = cell0 + i / Cin;
+        s_x[i] = (cell < cells) ? xin[cell * Cin + i % Cin] : 0.f;
+    }
+    if (threadIdx.x < LB_CELLS) s_valid[threadIdx.x] = (cell0 + threadIdx.x < cells) && cnt[cell0 + threadIdx.x] > 0;
+    __syncthreads();
+    const int groups = LB_CELLS / 4;
+    for (int t = threadIdx.x; t < Cout * groups; t += blockDim.x) {
+        const int o = t % Cout, jg = t / Cout;
+        const float *x0 = s_x + (size_t)(4 * jg) * Cin;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c0 = 0; c0 < Cin; c0 += 8) {
+            float w[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) w[u] = (c0 + u < Cin) ? __ldg(wT + (int64_t)(c0 + u) * Cout + o) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int c = min(c0 + u, Cin - 1);                      // clamped rows carry zero weights
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc[k] = fmaf(x0[(size_t)k * Cin + c], w[u], acc[k]);
+            }
         }
-        out[cell * Cout + o] = acc;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t cell = cell0 + 4 * jg + k;
+            if (cell >= cells) continue;
+            float v = 0.f;
+            if (s_valid[4 * jg + k]) v = scale ? fmaf(acc[k], scale[o], shift[o]) : acc[k];
+            out[cell * Cout + o] = v;
+        }
     }
 }
 
 extern "C" int dagr_grid_linear_bn(int64_t cells, const int32_t *cnt, const float *xin, int Cin, int Cout,
                                    const float *wT, const float *scale, const float *shift, float *out, void *stream)
 {
-    k_grid_linear_bn<<<dagr_div_up(cells, 4), 128, 0, (cudaStream_t)stream>>>(cells, cnt, xin, Cin, Cout, wT, scale, shift, out);
+    DAGR_CHECK_ARG(Cin > 0 && Cout > 0 && (size_t)LB_CELLS * Cin * 4 <= 48 * 1024, "bad channels");
+    if (cells <= 0) return DAGR_OK;
+    k_grid_linear_bn<<<dagr_div_up(cells, LB_CELLS), 256, (size_t)LB_CELLS * Cin * sizeof(float), (cudaStream_t)stream>>>(
+        cells, cnt, xin, Cin, Cout, wT, scale, shift, out);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }
@@ -576,7 +606,7 @@ extern "C" int dagr_grid_temporal_filter(const dagr_grid_t *gr, const int32_t *c
 // ------------------------------------------------------------------------------------------------
 // to_dense, decode, NMS
 // ------------------------------------------------------------------------------------------------
-__global__ void k_to_dense(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const float *__restrict__ x, int C,
+__global__ void k_to_dense(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const float *__restrict__ x, int C, int ldx,
                            const float *__restrict__ add, float *__restrict__ dense, int64_t total)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -586,16 +616,17 @@ __global__ void k_to_dense(const dagr_grid_t gr, const int32_t *__restrict__ cnt
     const int c = (int)((i / per) % C);
     const int b = (int)(i / ((int64_t)per * C));
     const int64_t cell = (int64_t)b * per + xy;
-    float v = cnt[cell] > 0 ? x[cell * C + c] : 0.f;
+    float v = cnt[cell] > 0 ? x[cell * ldx + c] : 0.f;
     if (add) v += add[i];
     dense[i] = v;
 }
 
-extern "C" int dagr_grid_to_dense(const dagr_grid_t *gr, const int32_t *cnt, const float *x, int C, const float *add,
+extern "C" int dagr_grid_to_dense(const dagr_grid_t *gr, const int32_t *cnt, const float *x, int C, int ldx, const float *add,
                                   float *dense, void *stream)
 {
     const int64_t total = (int64_t)gr->B * C * gr->ny * gr->nx;
-    k_to_dense<<<dagr_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(*gr, cnt, x, C, add, dense, total);
+    if (ldx == 0) ldx = C;
+    k_to_dense<<<dagr_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(*gr, cnt, x, C, ldx, add, dense, total);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }
@@ -626,19 +657,76 @@ extern "C" int dagr_head_decode(const float *reg, const float *obj, const float 
     return DAGR_OK;
 }
 
+// to_dense (spline_conv.py:80-107) of the three prediction convs + CNN maps (dagr.py:219-222) + collect_outputs /
+// decode_outputs (dagr.py:292-312) of one scale in ONE pass: per voxel of the dense head grid
+//   reg/obj/cls = (valid ? conv output : 0) + CNN map;  xy = (reg_xy + grid) * stride, wh = exp(reg_wh) * stride,
+//   sigmoid(obj), sigmoid(cls)  -> out[b, a0 + cell, 5 + nc]
+// (the separate to_dense + head_decode launches, 8 per forward, remain for callers that want the dense maps)
+__global__ void k_head_finish(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const float *__restrict__ cls, int ldc,
+                              const float *__restrict__ regobj, int ldr, const float *__restrict__ add_cls,
+                              const float *__restrict__ add_reg, const float *__restrict__ add_obj, int nc, float stride, int a0,
+                              int A, float *__restrict__ out)
+{
+    const int per = gr.ny * gr.nx;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= gr.B * per) return;
+    const int b = i / per, a = i % per, gy = a / gr.nx, gx = a % gr.nx;
+    const bool valid = cnt[i] > 0;
+    float r[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) r[c] = valid ? regobj[(int64_t)i * ldr + c] : 0.f;
+    if (add_reg) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) r[c] += add_reg[((int64_t)b * 4 + c) * per + a];
+    }
+    if (add_obj) r[4] += add_obj[(int64_t)b * per + a];
+    float *o = out + ((int64_t)b * A + a0 + a) * (5 + nc);
+    o[0] = (r[0] + (float)gx) * stride;
+    o[1] = (r[1] + (float)gy) * stride;
+    o[2] = expf(r[2]) * stride;
+    o[3] = expf(r[3]) * stride;
+    o[4] = 1.f / (1.f + expf(-r[4]));
+    for (int c = 0; c < nc; c++) {
+        float v = valid ? cls[(int64_t)i * ldc + c] : 0.f;
+        if (add_cls) v += add_cls[((int64_t)b * nc + c) * per + a];
+        o[5 + c] = 1.f / (1.f + expf(-v));
+    }
+}
+
+extern "C" int dagr_head_finish(const dagr_grid_t *gr, const int32_t *cnt, const float *cls, int ldc, const float *regobj, int ldr,
+                                const float *add_cls, const float *add_reg, const float *add_obj, int nc, int stride, int a0, int A,
+                                float *out, void *stream)
+{
+    DAGR_CHECK_ARG(gr && cls && regobj && ldc >= nc && ldr >= 5, "bad argument");
+    const int n = gr->B * gr->ny * gr->nx;
+    k_head_finish<<<dagr_div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(*gr, cnt, cls, ldc, regobj, ldr, add_cls, add_reg, add_obj, nc,
+                                                                       (float)stride, a0, A, out);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
 #define NMS_MAX 256
-__global__ void __launch_bounds__(256)
+#define NMS_THREADS 1024
+// One CTA of 32 warps per image.  The suppression matrix (which lower-ranked candidates would candidate i suppress) is
+// built warp-per-candidate: the 32 lanes test 32 lower-ranked candidates at once and a ballot packs the word, so the
+// longest dependent chain is ~6 x 6 IoUs instead of 175; ranking and the raw records are one pass over the anchors; only
+// the greedy walk over the ranking (torchvision.ops.nms semantics) is serial, over bit words in shared memory.
+__global__ void __launch_bounds__(NMS_THREADS)
 k_postprocess_nms(const float *__restrict__ pred, int A, int nc, float conf_thre, float nms_thre, float max_dim1,
                   int filtering, float *__restrict__ det, int32_t *__restrict__ ndet)
 {
     __shared__ float bx[NMS_MAX][4];     // class-offset boxes used for IoU
+    __shared__ float raw[NMS_MAX][6];    // x1, y1, x2, y2, score, class of every anchor
     __shared__ float sc[NMS_MAX];
     __shared__ short order[NMS_MAX];     // candidate ids in descending score order
     __shared__ unsigned char alive[NMS_MAX];
-    __shared__ int ncand;
+    __shared__ uint32_t supp[NMS_MAX][NMS_MAX / 32];
+    __shared__ short s_keep[NMS_MAX];
+    __shared__ int ncand, nout;
     const int b = blockIdx.x;
     const float *P = pred + (int64_t)b * A * (5 + nc);
     float *D = det + (int64_t)b * A * 6;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (threadIdx.x == 0) ncand = 0;
     __syncthreads();
     // per anchor: xyxy, class max, score, confidence mask (model/utils.py:62-87)
@@ -650,72 +738,68 @@ k_postprocess_nms(const float *__restrict__ pred, int A, int nc, float conf_thre
         for (int c = 1; c < nc; c++) if (p[5 + c] > cc) { cc = p[5 + c]; cl = c; }
         const float score = p[4] * cc;
         const bool keep = !filtering || (score * cc >= conf_thre);
-        // stash raw detection in the output slot a (compacted later)
-        D[a * 6 + 0] = x1; D[a * 6 + 1] = y1; D[a * 6 + 2] = x2; D[a * 6 + 3] = y2;
-        D[a * 6 + 4] = score; D[a * 6 + 5] = (float)cl;
+        raw[a][0] = x1; raw[a][1] = y1; raw[a][2] = x2; raw[a][3] = y2; raw[a][4] = score; raw[a][5] = (float)cl;
         const float offs = (float)cl * max_dim1;
         bx[a][0] = x1 + offs; bx[a][1] = y1 + offs; bx[a][2] = x2 + offs; bx[a][3] = y2 + offs;
         sc[a] = score;
         alive[a] = keep ? 1 : 0;
     }
     __syncthreads();
-    if (!filtering) { if (threadIdx.x == 0) ndet[b] = A; return; }
-    // rank among kept candidates: descending score, ties by anchor index
-    for (int a = threadIdx.x; a < A; a += blockDim.x) {
-        if (!alive[a]) continue;
-        int r = 0;
+    if (!filtering) {
+        for (int i = threadIdx.x; i < A * 6; i += blockDim.x) D[i] = raw[i / 6][i % 6];
+        if (threadIdx.x == 0) ndet[b] = A;
+        return;
+    }
+    // rank among kept candidates: descending score, ties by anchor index (one warp per anchor, lanes over the others)
+    for (int a = warp; a < A; a += nwarps) {
+        if (!alive[a]) continue;                                         // warp-uniform
         const float s = sc[a];
-        for (int j = 0; j < A; j++) if (alive[j] && (sc[j] > s || (sc[j] == s && j < a))) r++;
-        order[r] = (short)a;
-        atomicAdd(&ncand, 1);
+        int r = 0;
+        for (int j = lane; j < A; j += 32) r += (alive[j] && (sc[j] > s || (sc[j] == s && j < a))) ? 1 : 0;
+        r = __reduce_add_sync(0xffffffffu, r);
+        if (lane == 0) { order[r] = (short)a; atomicAdd(&ncand, 1); }
     }
     __syncthreads();
     const int n = ncand;
-    // greedy suppression in score order (torchvision.ops.nms semantics): every candidate first computes, in
-    // parallel, the bitmask of lower-ranked candidates it would suppress; one thread then walks the ranking.
-    __shared__ uint32_t supp[NMS_MAX][NMS_MAX / 32];
     const int nwords = (n + 31) / 32;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // suppression words: warp per candidate i, lane k of word wd tests candidate wd*32 + k (only those ranked below i)
+    for (int i = warp; i < n; i += nwarps) {
         const int ai = order[i];
         const float ax1 = bx[ai][0], ay1 = bx[ai][1], ax2 = bx[ai][2], ay2 = bx[ai][3];
         const float sa = (ax2 - ax1) * (ay2 - ay1);
-        for (int wd = 0; wd < nwords; wd++) {
-            uint32_t bits = 0;
-            for (int k = wd * 32; k < min(n, wd * 32 + 32); k++) {
-                if (k <= i) continue;
+        for (int wd = i >> 5; wd < nwords; wd++) {
+            const int k = wd * 32 + lane;
+            bool hit = false;
+            if (k > i && k < n) {
                 const int aj = order[k];
                 const float l = fmaxf(ax1, bx[aj][0]), t = fmaxf(ay1, bx[aj][1]);
                 const float r = fminf(ax2, bx[aj][2]), bt = fminf(ay2, bx[aj][3]);
                 const float iw = fmaxf(r - l, 0.f), ih = fmaxf(bt - t, 0.f);
                 const float inter = iw * ih;
                 const float sb = (bx[aj][2] - bx[aj][0]) * (bx[aj][3] - bx[aj][1]);
-                if (inter / (sa + sb - inter) > nms_thre) bits |= 1u << (k & 31);
+                hit = inter / (sa + sb - inter) > nms_thre;
             }
-            supp[i][wd] = bits;
+            const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) supp[i][wd] = bits;
         }
     }
     __syncthreads();
-    __shared__ short s_keep[NMS_MAX];
-    __shared__ int nout;
-    if (threadIdx.x == 0) {
-        uint32_t dead[NMS_MAX / 32];
-        for (int wd = 0; wd < nwords; wd++) dead[wd] = 0;
+    // greedy walk in score order: warp 0, lane wd keeps word wd of the dead mask
+    if (warp == 0) {
+        uint32_t dead = 0;
         int m = 0;
         for (int i = 0; i < n; i++) {
-            if ((dead[i >> 5] >> (i & 31)) & 1u) continue;
-            s_keep[m++] = order[i];
-            for (int wd = i >> 5; wd < nwords; wd++) dead[wd] |= supp[i][wd];
+            const uint32_t dw = __shfl_sync(0xffffffffu, dead, i >> 5);
+            if ((dw >> (i & 31)) & 1u) continue;                         // warp-uniform
+            if (lane == 0) s_keep[m] = order[i];
+            m++;
+            if (lane < nwords && lane >= (i >> 5)) dead |= supp[i][lane];
         }
-        nout = m;
+        if (lane == 0) nout = m;
     }
     __syncthreads();
-    // compact survivors in score order: gather into registers first (the raw records live in D itself)
-    float vals[(NMS_MAX * 6 + 255) / 256];
-    int cnt = 0;
-    for (int i = threadIdx.x; i < A * 6; i += blockDim.x, cnt++) vals[cnt] = (i / 6 < nout) ? D[s_keep[i / 6] * 6 + i % 6] : 0.f;
-    __syncthreads();
-    cnt = 0;
-    for (int i = threadIdx.x; i < A * 6; i += blockDim.x, cnt++) D[i] = vals[cnt];
+    // survivors in score order, zero padding behind them
+    for (int i = threadIdx.x; i < A * 6; i += blockDim.x) D[i] = (i / 6 < nout) ? raw[s_keep[i / 6]][i % 6] : 0.f;
     if (threadIdx.x == 0) ndet[b] = nout;
 }
 
@@ -724,7 +808,7 @@ extern "C" int dagr_postprocess_nms(const float *pred, int B, int A, int nc, flo
 {
     DAGR_CHECK_ARG(A > 0 && A <= NMS_MAX, "A must be in [1,256] (two-scale DAGR heads have 175 anchors)");
     const float max_dim1 = (float)((width > height ? width : height) + 1);
-    k_postprocess_nms<<<B, 256, 0, (cudaStream_t)stream>>>(pred, A, nc, conf_thre, nms_thre, max_dim1, filtering, det, ndet);
+    k_postprocess_nms<<<B, NMS_THREADS, 0, (cudaStream_t)stream>>>(pred, A, nc, conf_thre, nms_thre, max_dim1, filtering, det, ndet);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

@@ -44,6 +44,20 @@ class _ConvPack:
         self.relu = relu
 
 
+def _merge_packs(a: "_ConvPack", b: "_ConvPack") -> "_ConvPack":
+    """two SplineConvs over the SAME input evaluated as one conv with the output channels side by side."""
+    m = _ConvPack.__new__(_ConvPack)
+    assert a.cin == b.cin and a.relu == b.relu and (a.bias is None) == (b.bias is None) and (a.scale is None) == (b.scale is None)
+    m.cin, m.cout = a.cin, a.cout + b.cout
+    m.weight = torch.cat([a.weight, b.weight], dim=2).contiguous()
+    m.rootT = torch.cat([a.rootT, b.rootT], dim=1).contiguous()
+    m.bias = None if a.bias is None else torch.cat([a.bias, b.bias]).contiguous()
+    m.scale = None if a.scale is None else torch.cat([a.scale, b.scale]).contiguous()
+    m.shift = None if a.shift is None else torch.cat([a.shift, b.shift]).contiguous()
+    m.relu = a.relu
+    return m
+
+
 class _LayerPack:
     def __init__(self, layer, relu, dev):
         self.a = _ConvPack(layer.conv_block1.conv, layer.conv_block1.norm, relu, dev)
@@ -96,6 +110,7 @@ class Engine:
         self._geoms: Dict[tuple, Geometry] = {}
         self._pack = None
         self._pack_key = None
+        self._pack_gen = 0                   # bumped by every repack: captured graphs of older packs are never replayed
         self._sentinels = None
         self._ws: Dict[tuple, dict] = {}
         self.keep_node_features = False      # debug / parity: materialise per-event activations
@@ -123,7 +138,7 @@ class Engine:
     # kernels enqueued by each C-ABI call (see csrc/*.cu)
     _NKERNELS = dict(dagr_graph_sort=6, dagr_graph_sort_ring=6, dagr_stream_push=2, dagr_graph_search=1, dagr_l1_build=2, dagr_graph_export=5, dagr_l1_conv_a=1, dagr_l1_conv_b_pool=1, dagr_l1_conv_b_pool_voxel=2, dagr_l1_x0_image=1, dagr_xa_permute=1, dagr_l1_conv_a_image=2, dagr_voxel_sample_max=1,
                      dagr_pool1_finalize=1, dagr_grid_cat_pos=1, dagr_grid_conv=1, dagr_grid_linear_bn=1, dagr_grid_pool=1,
-                     dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1,
+                     dagr_grid_pool_finalize=1, dagr_grid_temporal_filter=1, dagr_grid_to_dense=1, dagr_head_decode=1, dagr_head_finish=1,
                      dagr_postprocess_nms=1, dagr_sample_features=1, dagr_denormalize_pos=1)
 
     def _run(self, label, fn, *args):
@@ -171,6 +186,12 @@ class Engine:
         self._pack = None
         self._pack_key = None
         self._sentinels = None
+        self._pack_gen += 1
+        for ws in self._ws.values():                         # captured coarse stacks hold pointers into the old pack
+            for sw in ws.get("slots", {}).values():
+                sw.pop("graph", None)
+                sw.pop("graph_key", None)
+                sw["graph_warm"] = 0
 
     def pack(self, geom: Geometry, device):
         key = (self._params_key(), tuple(geom.slots1), str(device))
@@ -181,16 +202,14 @@ class Engine:
         m = self.model
         bb, hd = m.backbone, m.head
         act = getattr(m.args, "activation", "relu")
-        if act != "relu":
-            raise NotImplementedError("dagr_b200 kernels implement activation=relu (all reference configs)")
         relu = True
         l1 = bb.conv_block1
         ca, cb = l1.conv_block1, l1.conv_block2
         slots = torch.tensor(geom.slots1, dtype=torch.long)
         cin0 = ca.conv.in_channels
-        if ca.conv.out_channels != 16 or cin0 not in (3, 19):
-            raise NotImplementedError("event-level kernels expect conv_block1 = Layer(3 -> 16) (events only) or "
-                                      "Layer(19 -> 16) (image fusion), base_width 0.5")
+        # every shape restriction of the kernels lives in ONE C-ABI call (include/dagr_b200.h: dagr_check_config)
+        if self.lib.dagr_check_config(C.byref(geom.c_geom), 0, int(cin0), int(ca.conv.out_channels), str(act).encode()) != 0:
+            raise NotImplementedError("dagr_b200: " + (self.lib.dagr_last_error() or b"").decode())
         pb = _lib.L1BParams()
         _fill(pb.w, cb.conv.weight.detach().cpu()[slots])                    # [15,16,16]
         _fill(pb.root, cb.conv.lin.weight.detach().cpu().t())
@@ -226,13 +245,19 @@ class Engine:
         for k in range(hd.num_scales):
             sfx = str(k + 1)
             stem, cc, rc = getattr(hd, "stem" + sfx), getattr(hd, "cls_conv" + sfx), getattr(hd, "reg_conv" + sfx)
-            heads.append(dict(stem=_ConvPack(stem.conv, stem.norm, relu, device),
-                              cls_conv=_ConvPack(cc.conv, cc.norm, relu, device),
-                              reg_conv=_ConvPack(rc.conv, rc.norm, relu, device),
-                              cls_pred=_ConvPack(getattr(hd, "cls_pred" + sfx), None, False, device),
-                              reg_pred=_ConvPack(getattr(hd, "reg_pred" + sfx), None, False, device),
-                              obj_pred=_ConvPack(getattr(hd, "obj_pred" + sfx), None, False, device)))
+            hp = dict(stem=_ConvPack(stem.conv, stem.norm, relu, device),
+                      cls_conv=_ConvPack(cc.conv, cc.norm, relu, device),
+                      reg_conv=_ConvPack(rc.conv, rc.norm, relu, device),
+                      cls_pred=_ConvPack(getattr(hd, "cls_pred" + sfx), None, False, device),
+                      reg_pred=_ConvPack(getattr(hd, "reg_pred" + sfx), None, False, device),
+                      obj_pred=_ConvPack(getattr(hd, "obj_pred" + sfx), None, False, device))
+            # convs that read the same tensor run as one launch: cls_conv | reg_conv (both on the stem output) and
+            # reg_pred | obj_pred (both on the reg_conv output), dagr.py:179-190
+            hp["clsreg_conv"] = _merge_packs(hp["cls_conv"], hp["reg_conv"])
+            hp["regobj_pred"] = _merge_packs(hp["reg_pred"], hp["obj_pred"])
+            heads.append(hp)
         pk["heads"] = heads
+        self._pack_gen += 1
         self._pack, self._pack_key = pk, key
         return pk
 
@@ -250,18 +275,14 @@ class Engine:
             dev = device
             nscan = max(geom.NK + 1, cap + 1)
             ws = dict(cap=cap)
-            ws["key"] = torch.empty(cap, dtype=torch.int32, device=dev)
-            ws["tmp"] = torch.empty(cap, dtype=torch.int32, device=dev)
-            ws["count"] = torch.zeros(geom.NK + 1, dtype=torch.int32, device=dev)
-            ws["blocksums"] = torch.empty(int(self.lib.dagr_scan_blocks(nscan)) + 2, dtype=torch.int32, device=dev)
-            ws["start"] = torch.empty(geom.NK + 1, dtype=torch.int32, device=dev)
-            ws["perm"] = torch.empty(cap, dtype=torch.int32, device=dev)
-            ws["ti"] = torch.empty((cap, 2), dtype=torch.int32, device=dev)
-            ws["xyb"] = torch.empty(cap, dtype=torch.int32, device=dev)
-            ws["feat_s"] = torch.empty(cap, dtype=torch.float32, device=dev)
-            ws["nbr"] = torch.empty(_lib.ELL * cap, dtype=torch.int32, device=dev)
-            ws["off"] = torch.empty(_lib.ELL * cap, dtype=torch.int16, device=dev)
-            ws["xa"] = torch.empty(cap * 16, dtype=torch.float32, device=dev)      # half-major [2][N][8]
+            sz = _lib.EventWs()                                   # the library states its own workspace sizes (bytes)
+            _lib.check(self.lib.dagr_event_workspace_bytes(C.byref(geom.c_geom), cap, C.byref(sz)), "event_workspace_bytes")
+            for name, dt in (("key", torch.int32), ("tmp", torch.int32), ("blocksums", torch.int32), ("start", torch.int32),
+                             ("perm", torch.int32), ("ti", torch.int32), ("xyb", torch.int32), ("feat_s", torch.float32),
+                             ("nbr", torch.int32), ("off", torch.int16), ("xa", torch.float32)):
+                ws[name] = torch.empty(int(getattr(sz, name)) // torch.empty(0, dtype=dt).element_size(), dtype=dt, device=dev)
+            ws["ti"] = ws["ti"].view(-1, 2)
+            ws["count"] = torch.zeros(int(sz.count) // 4, dtype=torch.int32, device=dev)      # zero on entry, zero again on exit
             ws["x1"] = None
             # zero-on-entry accumulators of all levels in ONE buffer (single memset per forward)
             C_lv = self.model.backbone.output_channels          # [16, 64, C, C, C]
@@ -274,19 +295,23 @@ class Engine:
                 sizes[name] = (off, nbytes)
                 off += nbytes
 
-            take("cellmask", geom.cells1 * 4)
+            take("cellmask", int(sz.cellmask))
             take("poolmax", geom.cells1 * 16 * 4)
+            bb = self.model.backbone
+            fc = list(getattr(getattr(bb, "net", None), "feature_channels", [])) if bb.use_image else []
             for lv in (1, 2, 3):
                 cells = geom.cells(lv)
-                Cc = C_lv[lv] + 64 * 3                          # channels pooled into this level (+ headroom for image features)
-                take(f"acc{lv}", cells * Cc * 8)
-                take(f"possum{lv}", cells * 3 * 8)
-                take(f"ptmax{lv}", cells * 4)
-                take(f"pcnt{lv}", cells * 4)
-                take(f"pmask{lv}", cells * 4)
+                Cc = C_lv[lv] + (fc[lv + 1] if bb.use_image else 0)      # channels pooled into this level (net.py:141-171)
+                psz = _lib.PoolWs()
+                _lib.check(self.lib.dagr_pool_workspace_bytes(cells, int(Cc), C.byref(psz)), "pool_workspace_bytes")
+                take(f"acc{lv}", int(psz.acc))
+                take(f"possum{lv}", int(psz.possum))
+                take(f"ptmax{lv}", int(psz.ptmax))
+                take(f"pcnt{lv}", int(psz.pcnt))
+                take(f"pmask{lv}", int(psz.pmask))
             take("wl_hdr", 32)                                   # dense-voxel work lists: (count, cursor) x {build, conv_a, conv_b}
             for wl in ("wl_build", "wl_conv_a", "wl_conv_b"):     # ... and the queued voxel ids
-                take(wl, geom.cells1 * 4)
+                take(wl, int(sz.wl_ids))
             take("err", 4)
             take("flags", 16)
             ws["zero_buf"] = torch.zeros(off, dtype=torch.uint8, device=dev)
@@ -343,8 +368,11 @@ class Engine:
             self._dense[id(ws.base)] = st
         if st["event"] is not None and st["event"].query():            # counts of an earlier forward have arrived (no waiting)
             h = st["host"]
+            cells = max(1, ws["grids"][0].cells)
             for k in range(3):
-                if int(h[2 * k]) > 0:
+                # worth two extra launches (~45 us even when the list is empty) once >= 5 % of the voxels are over capacity;
+                # a uniform 300 k-event sample has ~1 % of its voxels just above the conv kernel's 1344 rows
+                if int(h[2 * k]) * 20 >= cells:
                     st["defer"][k], st["quiet"][k] = 1, 0
                 elif st["defer"][k]:
                     st["quiet"][k] += 1
@@ -377,10 +405,10 @@ class Engine:
         return t[:n].view(*shape)
 
     # ------------------------------------------------------------------------------------------
-    def _grid_conv(self, geom, lv, gs: GridState, xin, pack: _ConvPack, skip, out, st):
+    def _grid_conv(self, geom, lv, gs: GridState, xin, pack: _ConvPack, skip, out, st, ldin=0):
         level = geom.levels[lv]
         self._run(f"grid_conv_L{lv + 1}_{pack.cin}x{pack.cout}", self.lib.dagr_grid_conv, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(gs.pxy), _lib.ptr(gs.mask),
-                                           _lib.ptr(xin), pack.cin, pack.cout, _lib.ptr(pack.weight), _lib.ptr(pack.rootT),
+                                           _lib.ptr(xin), int(ldin), pack.cin, pack.cout, _lib.ptr(pack.weight), _lib.ptr(pack.rootT),
                                            _lib.ptr(pack.bias), _lib.ptr(pack.scale), _lib.ptr(pack.shift),
                                            _lib.ptr(skip), 1 if pack.relu else 0, level.den_x, level.den_y,
                                            _lib.ptr(out), st)
@@ -409,6 +437,9 @@ class Engine:
         gp: GridState = ws["grids"][lp]
         Cc = x.shape[1]
         acc = self._zs(ws, f"acc{lp}", torch.uint8)
+        if gp.cells * Cc * 8 > acc.numel():
+            raise RuntimeError(f"dagr_b200: pooling accumulator of level {lp + 1} holds {acc.numel()} bytes, {gp.cells * Cc * 8} needed "
+                               f"({Cc} channels)")
         accmax = acc.view(torch.int32) if aggr == 0 else None
         accsum = acc.view(torch.float64) if aggr == 1 else None
         possum = self._zs(ws, f"possum{lp}", torch.float64)
@@ -453,7 +484,8 @@ class Engine:
 
     @torch.no_grad()
     def forward_events(self, batch_i32: torch.Tensor, pos_i32: torch.Tensor, feat: torch.Tensor, B: int,
-                       W: int, H: int, image_feats=None, image_outs=None, stream_state=None, n_old: int = 0, ring=None):
+                       W: int, H: int, image_feats=None, image_outs=None, stream_state=None, n_old: int = 0, ring=None,
+                       image_event=None):
         """batch int32[N], pos int32[N,3], feat fp32[N] (polarity) on CUDA -> decoded [B, A, 5+nc].
 
         ring = device control block (int32[8], dagr_graph_sort_ring): the three inputs are ring buffers of N = capacity
@@ -515,6 +547,8 @@ class Engine:
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), None, _lib.ptr(flags), 0, _lib.ptr(nbr), _lib.ptr(off),
                       _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_hdr), _lib.ptr(self._zs(ws, "wl_build", torch.int32)), defer[0], st)
+            if image_event is not None:                       # the image branch ran on a side stream next to sort + probe
+                torch.cuda.current_stream().wait_event(image_event)
             f0 = image_feats[0]
             x0 = self._buf(ws, "x0img", (3 * max(N, 1) * 8,), torch.float32, dev)
             skipv = self._buf(ws, "skipv", (max(N, 1), 16), torch.float32, dev)
@@ -565,6 +599,12 @@ class Engine:
                       _lib.ptr(poolmax), 16, _lib.ptr(g1.cnt), _lib.ptr(g1.pxy), _lib.ptr(g1.tmean), _lib.ptr(g1.tmax),
                       _lib.ptr(g1.x), st)
         g1.mask = cellmask[:g1.cells]
+        if kto and stream_state is not None:
+            # the persistent stream mask only ever gains edges; the temporal filter (pooling.py:69-72) depends on the CURRENT
+            # t_max of both voxels, so it must work on a per-step copy or edges dropped once could never come back
+            step_mask = self._zs(ws, "cellmask", torch.int32)
+            step_mask[:g1.cells].copy_(cellmask[:g1.cells])
+            g1.mask = step_mask[:g1.cells]
         if kto:
             self._run("temporal_filter", lib.dagr_grid_temporal_filter, C.byref(geom.levels[0].grid), _lib.ptr(g1.cnt), _lib.ptr(g1.tmax),
                                                      _lib.ptr(g1.mask), st)
@@ -598,31 +638,34 @@ class Engine:
                 nm = f"head{k}"
                 stem = self._buf(ws, nm + "_stem", (cells, hp["stem"].cout), torch.float32, dev)
                 self._grid_conv(geom, lv, gs, xo, hp["stem"], None, stem, st)
-                cf = self._buf(ws, nm + "_cf", (cells, hp["cls_conv"].cout), torch.float32, dev)
-                rf = self._buf(ws, nm + "_rf", (cells, hp["reg_conv"].cout), torch.float32, dev)
-                self._grid_conv(geom, lv, gs, stem, hp["cls_conv"], None, cf, st)
-                self._grid_conv(geom, lv, gs, stem, hp["reg_conv"], None, rf, st)
-                dense = {}
-                for name, src, cpk in (("cls", cf, hp["cls_pred"]), ("reg", rf, hp["reg_pred"]), ("obj", rf, hp["obj_pred"])):
-                    o = self._buf(ws, nm + "_" + name, (cells, cpk.cout), torch.float32, dev)
-                    self._grid_conv(geom, lv, gs, src, cpk, None, o, st)
-                    d = self._buf(ws, nm + "_d" + name, (B, cpk.cout, level.ny, level.nx), torch.float32, dev)
-                    add = None
-                    if image_outs is not None:
-                        add = image_outs[name + "_output"][k].float().contiguous()
-                    self._run("to_dense", lib.dagr_grid_to_dense, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(o), cpk.cout,
-                                                      _lib.ptr(add), _lib.ptr(d), st)
-                    dense[name] = d
+                Cf = hp["cls_conv"].cout
+                cr = self._buf(ws, nm + "_cr", (cells, 2 * Cf), torch.float32, dev)          # [cls_feat | reg_feat]
+                self._grid_conv(geom, lv, gs, stem, hp["clsreg_conv"], None, cr, st)
+                ocls = self._buf(ws, nm + "_cls", (cells, nc), torch.float32, dev)
+                self._grid_conv(geom, lv, gs, cr, hp["cls_pred"], None, ocls, st, ldin=2 * Cf)
+                oro = self._buf(ws, nm + "_regobj", (cells, 5), torch.float32, dev)         # [reg(4) | obj(1)]
+                self._grid_conv(geom, lv, gs, cr[:, Cf:], hp["regobj_pred"], None, oro, st, ldin=2 * Cf)
+                adds = {}
+                for name in ("cls", "reg", "obj"):
+                    adds[name] = image_outs[name + "_output"][k].float().contiguous() if image_outs is not None else None
                 stride = model.backbone.strides[k]
-                self._run("head_decode", lib.dagr_head_decode, _lib.ptr(dense["reg"]), _lib.ptr(dense["obj"]), _lib.ptr(dense["cls"]), B, nc,
-                                                level.ny, level.nx, int(stride), a0, A, _lib.ptr(out), st)
+                self._run("head_finish", lib.dagr_head_finish, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(ocls), nc, _lib.ptr(oro), 5,
+                          _lib.ptr(adds["cls"]), _lib.ptr(adds["reg"]), _lib.ptr(adds["obj"]), nc, int(stride), a0, A, _lib.ptr(out), st)
+                dense = {}
+                if self.keep_node_features:
+                    # parity / debugging: the dense [B,C,ny,nx] head maps of SplineConvToDense (spline_conv.py:80-107)
+                    for name, src, c0, cw, ld in (("cls", ocls, 0, nc, nc), ("reg", oro, 0, 4, 5), ("obj", oro, 4, 1, 5)):
+                        d = self._buf(ws, nm + "_d" + name, (B, cw, level.ny, level.nx), torch.float32, dev)
+                        self._run("to_dense", lib.dagr_grid_to_dense, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(src[:, c0:]), cw, ld,
+                                  _lib.ptr(adds[name]), _lib.ptr(d), st)
+                        dense[name] = d
                 a0 += level.nx * level.ny
                 dense_all.append(dense)
             return out, [g1, g2, g3, g4], inter, dense_all
 
         # The coarse stack is ~55 small, fixed-shape launches: replay it as ONE CUDA graph (captured on the second
         # call with identical buffers; the event-level kernels stay eager because their grids depend on N).
-        gkey = (id(ws.base), slot, id(pk), B, kto, cellmask.data_ptr())
+        gkey = (id(ws.base), slot, self._pack_gen, B, kto, cellmask.data_ptr(), bool(self.keep_node_features))
 
         def run_coarse():
             if self.use_graphs and self.prof is None and not use_image and ring is None:

@@ -92,6 +92,8 @@ class DAGR(YOLOX):
         self.time_window = int(getattr(args, "time_window_us", 1000000))
         self._engine = None
         self._async = None
+        self._image_branch = None
+        self.image_graph = True         # dense image branch as a replayed CUDA graph on a side stream (model/image_branch.py)
         self.keep_stream = False        # True: forward(reset=True) starts a stream that forward(reset=False) extends
         if "img_net_checkpoint" in args:
             sd = torch.load(args.img_net_checkpoint, map_location="cpu")["ema"]
@@ -108,13 +110,14 @@ class DAGR(YOLOX):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k in ("_engine", "_async") else copy.deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_engine", "_async", "_image_branch") else copy.deepcopy(v, memo)
         return new
 
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_engine"] = None
         d["_async"] = None
+        d["_image_branch"] = None
         return d
 
     # packed weights follow the module's tensors: repack after anything that can replace or rewrite them
@@ -122,12 +125,16 @@ class DAGR(YOLOX):
         out = super()._apply(fn, *a, **kw)
         if getattr(self, "_engine", None) is not None:
             self._engine.invalidate()
+        if getattr(self, "_image_branch", None) is not None:
+            self._image_branch.invalidate()                 # captured graphs hold the old parameter storages
         return out
 
     def load_state_dict(self, *a, **kw):
         out = super().load_state_dict(*a, **kw)
         if getattr(self, "_engine", None) is not None:
             self._engine.invalidate()
+        if getattr(self, "_image_branch", None) is not None:
+            self._image_branch.invalidate()
         return out
 
     @property
@@ -199,17 +206,17 @@ class DAGR(YOLOX):
             return self._async.step_decoded(x, batch_size=int(getattr(x, "num_graphs", 1) or 1))
         batch_i, pos_i, feat, W, H = self._prepare_events(x)
         B = int(getattr(x, "num_graphs", 0) or (int(x.batch.max()) + 1 if len(x.batch) else 1))
-        image_feats = image_outs = None
+        image_feats = image_outs = image_event = None
         if self.backbone.use_image:
-            # dense image trunk + CNN head stay torch/cuDNN (tensor cores allowed here only), net.py:110, dagr.py:205-206
-            with torch.no_grad():
-                feats, outs = self.backbone.net(x.image.float())
-                image_feats = [f.float().contiguous() for f in feats]
-                sizes = self.backbone.get_output_sizes()[-self.head.num_scales:]
-                cnn_in = [torch.nn.functional.interpolate(o, size=tuple(sz)) for o, sz in zip(outs[-self.head.num_scales:], sizes)]
-                image_outs = self.head.cnn_head(cnn_in)
+            # dense image trunk + CNN head stay torch/cuDNN (tensor cores allowed here only), net.py:110, dagr.py:205-206;
+            # they run on a side stream, concurrently with the sort + radius-graph kernels below
+            if self._image_branch is None:
+                from .image_branch import ImageBranch
+                self._image_branch = ImageBranch(self)
+            image_feats, image_outs, image_event = self._image_branch.run(x.image, use_graph=self.image_graph)
             self.last_image_outs, self.last_image_feats = image_outs, image_feats
-        return self.engine.forward_events(batch_i, pos_i, feat, B, W, H, image_feats=image_feats, image_outs=image_outs)
+        return self.engine.forward_events(batch_i, pos_i, feat, B, W, H, image_feats=image_feats, image_outs=image_outs,
+                                          image_event=image_event)
 
     def forward(self, x, reset=True, return_targets=True, filtering=True):
         if self.training:

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DAGR_ABI_VERSION 1
+#define DAGR_ABI_VERSION 2
 
 #define DAGR_OK            0
 #define DAGR_E_ARG        -1   /* bad argument / unsupported shape        */
@@ -55,6 +55,28 @@ typedef struct {
     const float   *tabx;           /* [2r+1][4] x factor of the slot weights: tab[c][k+3j] = tabx[dx+r][k]*taby[dy+r][j] */
     const float   *taby;           /* [2r+1][8] y factor (5 used)                                     */
 } dagr_geom_t;
+
+/* ---------------------------------------------------------------------------------------------
+ * Argument contract and workspace sizes (the library never allocates; SURVEY 8(b): "workspace sizes via
+ * *_workspace_bytes").  All host-only: no CUDA call is made.
+ *
+ *   dagr_check_config           : every shape restriction of the kernels in one place.  cin0 / cout0 = channels of
+ *                                 conv_block1.conv_block1 (3 -> 16 events only, 19 -> 16 with image fusion), activation = the
+ *                                 yaml `activation` key.  Returns DAGR_OK or DAGR_E_UNSUPPORTED with dagr_last_error() set.
+ *   dagr_event_workspace_bytes  : byte sizes of every event-level buffer for N events (ELL leading dimension = N).
+ *   dagr_pool_workspace_bytes   : byte sizes of the zero-on-entry accumulators dagr_grid_pool needs for `channels` pooled
+ *                                 channels on the parent grid.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t key, tmp, count, blocksums, start, perm, ti, xyb, feat_s;   /* dagr_graph_sort[_ring]                    */
+    int64_t nbr, off, cellmask, xa;                                     /* dagr_l1_build (ELL adjacency, activations)  */
+    int64_t wl_hdr, wl_ids;                                             /* one dense-voxel work list (hdr zeroed)      */
+    int64_t x1;                                                         /* optional per-event conv_block1 output       */
+} dagr_event_ws_t;
+typedef struct { int64_t acc, possum, ptmax, pcnt, pmask; } dagr_pool_ws_t;
+int dagr_check_config(const dagr_geom_t *g, int64_t N, int cin0, int cout0, const char *activation);
+int dagr_event_workspace_bytes(const dagr_geom_t *g, int64_t N, dagr_event_ws_t *out);
+int dagr_pool_workspace_bytes(int64_t parent_cells, int channels, dagr_pool_ws_t *out);
 
 /* ---------------------------------------------------------------------------------------------
  * a1'  denormalize_pos  (src/dagr/model/layers/ev_tgn.py:11-16):  (pos*[W,H,T] + 1e-3).int()
@@ -263,7 +285,9 @@ int dagr_grid_cat_pos(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *
  *   attr = d/den + 0.5 with den_x = fl(2*M*W), den_y = fl(2*M*H)  (spline_conv.py:28-29)
  */
 int dagr_grid_conv(const dagr_grid_t *gr, const int32_t *cnt, const int32_t *pxy, const uint32_t *mask,
-                   const float *xin, int Cin, int Cout, const float *weight, const float *rootT,
+                   const float *xin, int ldin /* row stride of xin in floats (0 = Cin): the input may be a column block of a
+                                                 wider array, e.g. one half of the fused cls_conv|reg_conv output */,
+                   int Cin, int Cout, const float *weight, const float *rootT,
                    const float *bias, const float *scale, const float *shift, const float *skip,
                    int relu, float den_x, float den_y, float *out, void *stream);
 
@@ -294,13 +318,20 @@ int dagr_grid_temporal_filter(const dagr_grid_t *gr, const int32_t *cnt, const f
                               uint32_t *mask, void *stream);
 
 /* a10 to_dense (spline_conv.py:80-107): grid-major [cells, C] -> dense [B, C, ny, nx] (+= add, optional) */
-int dagr_grid_to_dense(const dagr_grid_t *gr, const int32_t *cnt, const float *x, int C,
+int dagr_grid_to_dense(const dagr_grid_t *gr, const int32_t *cnt, const float *x, int C, int ldx /* row stride of x, 0 = C */,
                        const float *add /*[B,C,ny,nx] or NULL*/, float *dense, void *stream);
 
 /* a11 collect_outputs + decode_outputs (dagr.py:292-312): per scale reg[B,4,h,w], obj[B,1,h,w],
  * cls[B,nc,h,w] -> out[B, A, 5+nc] rows [a0, a0+h*w)  */
 int dagr_head_decode(const float *reg, const float *obj, const float *cls, int B, int nc, int h, int w,
                      int stride, int a0, int A, float *out, void *stream);
+
+/* to_dense of the three prediction convs + the CNN head maps (dagr.py:219-222) + collect_outputs + decode_outputs of one
+ * scale in one launch: cls f32[cells, ldc] (nc used), regobj f32[cells, ldr] = (reg[4], obj[1]) as written by ONE conv over the
+ * concatenated reg_pred|obj_pred weights; add_* [B,C,ny,nx] or NULL -> out[B, A, 5+nc] rows [a0, a0 + ny*nx) */
+int dagr_head_finish(const dagr_grid_t *gr, const int32_t *cnt, const float *cls, int ldc, const float *regobj, int ldr,
+                     const float *add_cls, const float *add_reg, const float *add_obj, int nc, int stride, int a0, int A,
+                     float *out, void *stream);
 
 /* a11 postprocess_network_output + batched_nms_coordinate_trick (model/utils.py:25-33,61-110).
  * pred f32[B,A,5+nc] (decoded, cxcywh) -> det f32[B,A,6] = (x1,y1,x2,y2,score,label) compacted in

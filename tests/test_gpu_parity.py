@@ -421,14 +421,15 @@ def test_image_fusion_parity_vs_oracle(W, H, B, n, size):
     _check_forward(model, args, data, B, H, W, image=True, check_public=False)
 
 
-@pytest.mark.parametrize("W,H,B,n,chunks", [(240, 180, 1, 8000, [7999, 1]), (640, 480, 2, 30000, [0.5, 0.2, 0.2, 0.1])])
-def test_async_incremental_equals_dense(W, H, B, n, chunks):
+@pytest.mark.parametrize("W,H,B,n,chunks,kto", [(240, 180, 1, 8000, [7999, 1], False), (640, 480, 2, 30000, [0.5, 0.2, 0.2, 0.1], False),
+                                                  (320, 215, 1, 12000, [0.4, 0.3, 0.3], True)])
+def test_async_incremental_equals_dense(W, H, B, n, chunks, kto):
     """the reference's own invariant (evaluate_flops.py:90,139-147): init on N-1 events + 1-event update == dense
     forward on N events; generalised to several chunks and to B > 1 (tolerance 1e-5 instead of 1e-3)."""
     from dagr_b200.asynchronous import AsyncDAGR
     from dagr_b200.data import EventBatch
     from dagr_b200 import export
-    model, args = make_model("n", H, W)
+    model, args = make_model("n", H, W, keep_temporal_ordering=kto)
     model.cuda()
     raw, data = make_inputs(B, n, W, H, seed=5, kind="clustered")
     dense, _, _ = _run_graph(model, data, B)

@@ -215,7 +215,7 @@ def test_capi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dagr_b200.h but not exported"
     assert set(_lib.EXPORTS) == declared
-    assert lib.dagr_abi_version() == 1
+    assert lib.dagr_abi_version() == 2
 
 
 def test_product_has_no_cpu_fallback_and_never_imports_oracle():
@@ -350,3 +350,32 @@ def test_detection_records_match_the_reference_golden(tmp_path):
         assert r.dtype == ref.dtype and np.array_equal(r, ref)
 
 
+
+
+def test_capi_check_config_and_workspace_sizes():
+    """dagr_check_config states every kernel restriction in one call; *_workspace_bytes lets a foreign caller size buffers."""
+    import ctypes as C
+    from dagr_b200 import _lib
+    from dagr_b200.geometry import Geometry
+    lib = _lib.load()
+    geom = Geometry(640, 480, 8, device="cpu")
+    g = C.byref(geom.c_geom)
+    assert lib.dagr_check_config(g, 2_400_000, 3, 16, b"relu") == 0
+    assert lib.dagr_check_config(g, 2_400_000, 19, 16, None) == 0
+    for bad, needle in (((g, 1 << 24, 3, 16, b"relu"), "24 bits"), ((g, 10, 5, 16, b"relu"), "conv_block1"), ((g, 10, 3, 32, b"relu"), "conv_block1"),
+                        ((g, 10, 3, 16, b"elu"), "relu")):
+        assert lib.dagr_check_config(*bad) == -3
+        assert needle in lib.dagr_last_error().decode()
+    big = Geometry(640, 480, 8, device="cpu")
+    big.c_geom.K = 17
+    assert lib.dagr_check_config(C.byref(big.c_geom), 10, 3, 16, b"relu") == -3 and "max_neighbors" in lib.dagr_last_error().decode()
+    N = 2_400_000
+    sz = _lib.EventWs()
+    assert lib.dagr_event_workspace_bytes(g, N, C.byref(sz)) == 0
+    cells = 8 * 56 * 40
+    assert (sz.key, sz.perm, sz.ti, sz.nbr, sz.off, sz.xa) == (4 * N, 4 * N, 8 * N, 64 * N, 32 * N, 64 * N)
+    assert sz.start == 4 * (geom.NK + 1) and sz.count == sz.start and sz.cellmask == 4 * cells and sz.wl_ids == 4 * cells
+    assert sz.blocksums == 4 * (int(lib.dagr_scan_blocks(max(geom.NK + 1, N + 1))) + 2)
+    ps = _lib.PoolWs()
+    assert lib.dagr_pool_workspace_bytes(8 * 28 * 20, 64, C.byref(ps)) == 0
+    assert (ps.acc, ps.possum, ps.pcnt) == (8 * 28 * 20 * 64 * 8, 8 * 28 * 20 * 24, 8 * 28 * 20 * 4)
