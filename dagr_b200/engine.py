@@ -131,6 +131,7 @@ class Engine:
         # reset=True forwards; everything else silently takes the serial path.
         self.overlap = False
         self._cstream = None
+        self._fstream = None                 # forked branch of the coarse stack (first head scale)
         self._slot = 0
         self._done = [None, None]
         self._out_slot = {}
@@ -621,17 +622,14 @@ class Engine:
             _, _, o3 = self._layer(geom, 1, g2, lay[1], ws, "layer3", st, dev)
             g3 = self._pool(geom, 1, g2, cat_img(1, g2, o3, 3), aggr_cfg, ws, st, dev, kto)
             _, _, o4 = self._layer(geom, 2, g3, lay[2], ws, "layer4", st, dev)           # out3
-            g4 = self._pool(geom, 2, g3, cat_img(2, g3, o4, 4), 1, ws, st, dev, kto)     # pool4 is always mean (net.py:96-97)
-            _, _, o5 = self._layer(geom, 3, g4, lay[3], ws, "layer5", st, dev)           # out4
-            inter.update(o2=o2, o3=o3, o4=o4, o5=o5)
-            # ---- head ----------------------------------------------------------------------------
             nc = model.backbone.num_classes
-            scales = [(2, g3, o4), (3, g4, o5)][-model.head.num_scales:]
-            A = sum(geom.levels[lv].nx * geom.levels[lv].ny for lv, _, _ in scales)
+            nscale = model.head.num_scales
+            A = sum(geom.levels[lv].nx * geom.levels[lv].ny for lv in ((2, 3) if nscale == 2 else (3,)))
             out = self._buf(ws, "decoded", (B, A, 5 + nc), torch.float32, dev)
-            a0 = 0
-            dense_all = []
-            for k, (lv, gs, xo) in enumerate(scales):
+            dense_all = [None] * nscale
+
+            def head_scale(k, lv, gs, xo, a0, st):
+                """GNNHead.process_feature + collect_outputs + decode_outputs of one scale (dagr.py:179-312)."""
                 hp = pk["heads"][k]
                 level = geom.levels[lv]
                 cells = gs.cells
@@ -659,8 +657,30 @@ class Engine:
                         self._run("to_dense", lib.dagr_grid_to_dense, C.byref(level.grid), _lib.ptr(gs.cnt), _lib.ptr(src[:, c0:]), cw, ld,
                                   _lib.ptr(adds[name]), _lib.ptr(d), st)
                         dense[name] = d
-                a0 += level.nx * level.ny
-                dense_all.append(dense)
+                dense_all[k] = dense
+
+            # The first head scale only needs layer4's output: it runs on a forked stream next to pool4 + layer5 + the second
+            # scale (all of them are single-wave kernels on <= B*140 voxels, so they share the GPU instead of queueing);
+            # fork / join through events is captured like any other dependency when this stack is replayed as a graph.
+            join_ev = None
+            if nscale == 2:
+                cur = torch.cuda.current_stream()
+                if self._fstream is None:
+                    self._fstream = torch.cuda.Stream(device=dev, priority=-1)
+                fork_ev = torch.cuda.Event()
+                fork_ev.record(cur)
+                with torch.cuda.stream(self._fstream):
+                    self._fstream.wait_event(fork_ev)
+                    head_scale(0, 2, g3, o4, 0, _lib.stream_ptr())
+                    join_ev = torch.cuda.Event()
+                    join_ev.record(self._fstream)
+            g4 = self._pool(geom, 2, g3, cat_img(2, g3, o4, 4), 1, ws, st, dev, kto)     # pool4 is always mean (net.py:96-97)
+            _, _, o5 = self._layer(geom, 3, g4, lay[3], ws, "layer5", st, dev)           # out4
+            inter.update(o2=o2, o3=o3, o4=o4, o5=o5)
+            a0 = geom.levels[2].nx * geom.levels[2].ny if nscale == 2 else 0
+            head_scale(nscale - 1, 3, g4, o5, a0, st)
+            if join_ev is not None:
+                torch.cuda.current_stream().wait_event(join_ev)
             return out, [g1, g2, g3, g4], inter, dense_all
 
         # The coarse stack is ~55 small, fixed-shape launches: replay it as ONE CUDA graph (captured on the second

@@ -17,6 +17,7 @@ class ImageBranch:
     def __init__(self, model):
         self.model = model
         self.stream = None
+        self._sizes = None         # head grid sizes: read once (a device->host read is not allowed under graph capture)
         self._graphs = {}          # (B, C, H, W, device) -> dict(graph, inp, feats, outs, warm)
 
     def invalidate(self):
@@ -26,7 +27,9 @@ class ImageBranch:
         m = self.model
         feats, outs = m.backbone.net(image)
         feats = [f.float().contiguous() for f in feats]
-        sizes = m.backbone.get_output_sizes()[-m.head.num_scales:]
+        if self._sizes is None:
+            self._sizes = m.backbone.get_output_sizes()[-m.head.num_scales:]
+        sizes = self._sizes
         cnn_in = [torch.nn.functional.interpolate(o, size=tuple(sz)) for o, sz in zip(outs[-m.head.num_scales:], sizes)]
         image_outs = m.head.cnn_head(cnn_in)
         return feats, {k: [t.float().contiguous() for t in v] for k, v in image_outs.items()}
