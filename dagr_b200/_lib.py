@@ -122,9 +122,16 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not _LIB_PATH.exists():
+    if not os.environ.get("DAGR_B200_LIB"):
         from . import build as _build
-        _build.build()
+        if _build.needs_build():                          # missing, or built from other sources than the ones in the tree
+            try:
+                _build.build(force=True)
+            except Exception as e:
+                if not _LIB_PATH.exists():
+                    raise RuntimeError(f"dagr_b200: could not build the CUDA extension: {e}") from e
+                import warnings
+                warnings.warn(f"dagr_b200: libdagr_b200.so is older than its sources and could not be rebuilt ({e})")
     if not _LIB_PATH.exists():
         raise RuntimeError(f"dagr_b200: CUDA extension {_LIB_PATH} is missing and could not be built; "
                            "there is no CPU fallback")

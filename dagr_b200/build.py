@@ -22,12 +22,26 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+HASHFILE = PKG / "libdagr_b200.srchash"
+
+
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    deps = [CSRC / s for s in SOURCES] + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dagr_b200.h"]
+    for d in deps:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not LIB.exists():
+    """the library is stale when the sources' content hash differs from the one recorded at build time (mtimes do not
+    survive a copy of the tree to another box)."""
+    if not LIB.exists() or not HASHFILE.exists():
         return True
-    t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dagr_b200.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+    return HASHFILE.read_text().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -52,6 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (bdir / "ptxas.log").write_text("\n".join(log))
     cmd = [nvcc, "-shared", "-o", str(LIB)] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
+    HASHFILE.write_text(_source_hash() + "\n")
     if verbose:
         print("\n".join(log))
     return LIB

@@ -548,8 +548,8 @@ class Engine:
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
                       _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), None, _lib.ptr(flags), 0, _lib.ptr(nbr), _lib.ptr(off),
                       _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_hdr), _lib.ptr(self._zs(ws, "wl_build", torch.int32)), defer[0], st)
-            if image_event is not None:                       # the image branch ran on a side stream next to sort + probe
-                torch.cuda.current_stream().wait_event(image_event)
+            if image_event is not None:                       # stage 1 of the image branch ran on a side stream next to sort + probe
+                torch.cuda.current_stream().wait_event(image_event[0])
             f0 = image_feats[0]
             x0 = self._buf(ws, "x0img", (3 * max(N, 1) * 8,), torch.float32, dev)
             skipv = self._buf(ws, "skipv", (max(N, 1), 16), torch.float32, dev)
@@ -618,6 +618,8 @@ class Engine:
                 return self._append_image(geom, lv, gs, o, image_feats[k], ws, st, dev) if use_image else o
 
             _, _, o2 = self._layer(geom, 0, g1, lay[0], ws, "layer2", st, dev)
+            if use_image and image_event is not None:         # layer2..4 taps + CNN head maps (stage 2 of the image branch)
+                torch.cuda.current_stream().wait_event(image_event[1])
             g2 = self._pool(geom, 0, g1, cat_img(0, g1, o2, 2), aggr_cfg, ws, st, dev, kto)
             _, _, o3 = self._layer(geom, 1, g2, lay[1], ws, "layer3", st, dev)
             g3 = self._pool(geom, 1, g2, cat_img(1, g2, o3, 3), aggr_cfg, ws, st, dev, kto)

@@ -57,3 +57,31 @@ class HookModule(nn.Module):
         if len(self.output_dconv) > 0:
             outs = [d(o) for o, d in zip(outs, self.output_dconv)]
         return feats, outs
+
+    # The same forward in two stages (dagr_b200/model/image_branch.py): the event-level kernels only sample the conv1 and
+    # layer1 taps, so they can start while layer2..4 are still running.
+    def stage1(self, x):
+        """-> (feature maps of the taps up to layer1, trunk activation after layer1)"""
+        assert self.feature_layers[:2] == ["conv1", "layer1"] and not set(self.output_layers) & {"conv1", "layer1"}
+        m = self.module
+        c1 = m.conv1(x)
+        l1 = m.layer1(m.maxpool(m.relu(m.bn1(c1))))
+        taps = [c1, l1]
+        if len(self.feature_dconv) > 0:
+            taps = [self.feature_dconv[i](t) for i, t in enumerate(taps)]
+        return taps, l1
+
+    def stage2(self, l1):
+        """-> (feature maps of the remaining taps, output taps)"""
+        m = self.module
+        taps = {}
+        x = m.layer2(l1); taps["layer2"] = x
+        x = m.layer3(x); taps["layer3"] = x
+        x = m.layer4(x); taps["layer4"] = x
+        feats = [taps[l] for l in self.feature_layers[2:]]
+        outs = [taps[l] for l in self.output_layers]
+        if len(self.feature_dconv) > 0:
+            feats = [self.feature_dconv[2 + i](f) for i, f in enumerate(feats)]
+        if len(self.output_dconv) > 0:
+            outs = [d(o) for o, d in zip(outs, self.output_dconv)]
+        return feats, outs

@@ -16,7 +16,7 @@ for tag, prefix in want.items():
     body = next(f for f in funcs if f.lstrip().startswith("Function : " + prefix))
     hist = collections.Counter()
     for line in body.splitlines():
-        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+        m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
         if m:
             op = m.group(1)
             keep_suffix = op.startswith(("LDCU", "LDS", "UBLKCP", "SYNCS", "STS", "LDG", "STG"))
@@ -27,5 +27,13 @@ for tag, prefix in want.items():
     tensor = [k for k in hist if k.startswith(("UTC", "HMMA", "IMMA", "QGMMA", "UTMALDG"))]
     out.append(f"# tensor-core / tensor-map instructions: {tensor or 'none'}")
     out.append("")
-    (ROOT / "profiles" / f"r02_sass_{tag}.txt").write_text("\n".join(out) + body)
+    # listing without the encoding columns: "/*addr*/ INSTR ;"
+    lines = []
+    for line in body.splitlines():
+        m = re.match(r"\s+(/\*[0-9a-f]{4,6}\*/\s+.*?;)\s*/\*", line)
+        if m:
+            lines.append("    " + re.sub(r"\s{2,}", "  ", m.group(1)))
+        elif "Function :" in line or ".headerflags" in line:
+            lines.append(line.strip())
+    (ROOT / "profiles" / f"r02_sass_{tag}.txt").write_text("\n".join(out + lines) + "\n")
     print(tag, total, hist.most_common(12))
