@@ -215,8 +215,32 @@ class DAGR(YOLOX):
                 self._image_branch = ImageBranch(self)
             image_feats, image_outs, image_event = self._image_branch.run(x.image, use_graph=self.image_graph)
             self.last_image_outs, self.last_image_feats = image_outs, image_feats
+            if self.head.no_events:
+                # --no_events (dagr.py:284): detections from the image branch alone -- collect_outputs + decode_outputs on
+                # the CNN head maps (tiny dense tensors; plain torch on the current stream)
+                torch.cuda.current_stream().wait_event(image_event[1])
+                return self._decode_image_only(image_outs)
+        elif self.head.no_events:
+            raise RuntimeError("--no_events needs --use_image (the reference would fail on the missing image branch too)")
         return self.engine.forward_events(batch_i, pos_i, feat, B, W, H, image_feats=image_feats, image_outs=image_outs,
                                           image_event=image_event)
+
+    def _decode_image_only(self, image_outs):
+        """GNNHead.collect_outputs + decode_outputs (dagr.py:292-312) for image_out['outputs']."""
+        outs, grids, strides = [], [], []
+        for k in range(self.head.num_scales):
+            reg, obj, cls = (image_outs[n + "_output"][k] for n in ("reg", "obj", "cls"))
+            o = torch.cat([reg, obj.sigmoid(), cls.sigmoid()], 1)
+            h, w = o.shape[-2:]
+            yv, xv = torch.meshgrid(torch.arange(h, device=o.device), torch.arange(w, device=o.device), indexing="ij")
+            grids.append(torch.stack((xv, yv), 2).view(1, -1, 2).float())
+            strides.append(torch.full((1, h * w, 1), float(self.backbone.strides[k]), device=o.device))
+            outs.append(o.flatten(start_dim=2))
+        out = torch.cat(outs, dim=2).permute(0, 2, 1).contiguous()
+        grid, stride = torch.cat(grids, 1), torch.cat(strides, 1)
+        out[..., :2] = (out[..., :2] + grid) * stride
+        out[..., 2:4] = torch.exp(out[..., 2:4]) * stride
+        return out
 
     def forward(self, x, reset=True, return_targets=True, filtering=True):
         if self.training:

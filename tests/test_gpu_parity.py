@@ -776,3 +776,22 @@ def test_streaming_window_equals_dense_forward_on_live_window():
             assert torch.equal(out[0]["boxes"], want["boxes"].cpu()) and torch.equal(out[0]["scores"], want["scores"].cpu())
             checked += 1
     assert checked == 9 and det.graph is not None
+
+
+def test_no_events_returns_the_image_only_head_like_the_reference():
+    """--no_events (dagr.py:284): the detector outputs come from the CNN head maps alone (collect_outputs + decode_outputs)."""
+    from dagr_b200.data import format_data, synth_batch
+    from oracle import ref_ops as R
+    W, H, B = 240, 180, 2
+    model, args = make_model("n", H, W, use_image=True, img_net="resnet18", no_events=True, batch_size=B)
+    model.cuda()
+    data = format_data(synth_batch(B, 3000, W, H, seed=3, with_image=True).clone())
+    dec = model.forward_decoded(data.clone().cuda())
+    torch.cuda.synchronize()
+    outs = {k: [t.cpu() for t in v] for k, v in model.last_image_outs.items()}
+    maps = [torch.cat([outs["reg_output"][k], torch.sigmoid(outs["obj_output"][k]), torch.sigmoid(outs["cls_output"][k])], 1) for k in range(2)]
+    want = R.decode_outputs(torch.cat([m.flatten(start_dim=2) for m in maps], dim=2).permute(0, 2, 1), [m.shape[-2:] for m in maps],
+                            model.backbone.strides)
+    assert_close(dec.cpu(), want, tol=1e-6, what="no_events decoded")
+    dets = model(data.clone().cuda())[0]
+    assert len(dets) == B
