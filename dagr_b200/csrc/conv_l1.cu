@@ -394,8 +394,10 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
 #define CB2_UNROLL 1                                                    // measured: 1 -> 1.49 ms, 2 -> 1.56, 3 -> 1.58, 4 -> 1.68 (registers, I-cache)
 #endif
         constexpr int kUnroll = CB2_UNROLL;
+        // n carries the staged loop bounds: bits 0..7 = first entry, bits 8..15 = end (exclusive); see the ELL staging
+        const int q_end = n >> 8;
 #pragma unroll kUnroll
-        for (int q = 0; q <= n; q++) {
+        for (int q = n & 0xff; q < q_end; q++) {
             const uint32_t ell = s_ell[q * THREADS + tix];
             const uint32_t ro = ell & 0x3fff0u, xo = (ell >> 14) & 0x1f0u, yo = (ell >> 18) & 0x3e0u;
             const float4 t0 = *reinterpret_cast<const float4 *>(rb + ro), t1 = *reinterpret_cast<const float4 *>(rb + (ro ^ 16u));
@@ -497,6 +499,7 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
     float4 *s_wy = (float4 *)(s_wx + 128);                               // [2r+1][2]   y factor
     uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [16][THREADS]  slot 0 = self loop
     uint16_t *s_sp = (uint16_t *)(s_ell + DAGR_ELL * THREADS);           // [ncell]  (dx + r) | (dy + r) << 5
+    uint16_t *s_bnd = s_sp + ((g.ncell + 7) & ~7);                          // [THREADS]  per node: n_lo | (n_lo + n_mid) << 8  (see the staging below)
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
     const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
@@ -576,13 +579,34 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
                 jj[q] = (q < n) ? nbr[(int64_t)q * N + p] : 0;
                 cc[q] = (q < n) ? (int)off[(int64_t)q * N + p] : 0;
             }
+            // The edges are laid out by which x-slots they feed: degree-1 splines give every offset at most two adjacent
+            // non-zero x factors, so an edge left of the node (only x-slot 0 and 1) contributes exact zeros to the pass of
+            // x-slot 2 and vice versa.  Order: [slot-0 side | both / centre (incl. the self loop) | slot-2 side]; the pass of
+            // x-slot 0 then stops before the third group and the pass of x-slot 2 starts after the first (a third fewer row
+            // gathers and FMAs; skipped terms are exact zeros).
+            int cls[DAGR_ELL - 1];
+            int n_lo = 0, n_mid = 1;
 #pragma unroll
             for (int q = 0; q < DAGR_ELL - 1; q++) {
-                const int j = jj[q];
-                const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
-                s_ell[(q + 1) * THREADS + tix] = ((uint32_t)(2 * row + XA_SWZ(j)) << 4) | ((uint32_t)s_sp[cc[q]] << 18);
+                const uint32_t sp = s_sp[cc[q]];
+                cc[q] = (int)sp;
+                const float4 wxr = reinterpret_cast<const float4 *>(s_wx)[sp & 31u];
+                const bool has0 = wxr.x != 0.f, has2 = wxr.z != 0.f;
+                cls[q] = (has0 && !has2) ? 0 : ((has2 && !has0) ? 2 : 1);
+                if (q < n) { n_lo += cls[q] == 0; n_mid += cls[q] == 1; }
             }
-            s_ell[tix] = ((uint32_t)(2 * (p + d1) + XA_SWZ(p)) << 4) | ((uint32_t)(g.r | (g.r << 5)) << 18);   // self loop
+            int c0 = 0, c1 = n_lo, c2 = n_lo + n_mid;
+            s_ell[(c1++) * THREADS + tix] = ((uint32_t)(2 * (p + d1) + XA_SWZ(p)) << 4) | ((uint32_t)(g.r | (g.r << 5)) << 18);   // self loop
+#pragma unroll
+            for (int q = 0; q < DAGR_ELL - 1; q++) {
+                if (q < n) {
+                    const int j = jj[q];
+                    const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
+                    const int slot = cls[q] == 0 ? c0++ : (cls[q] == 1 ? c1++ : c2++);
+                    s_ell[slot * THREADS + tix] = ((uint32_t)(2 * row + XA_SWZ(j)) << 4) | ((uint32_t)cc[q] << 18);
+                }
+            }
+            s_bnd[tix] = (uint16_t)(n_lo | ((n_lo + n_mid) << 8));
         }
         float2 o2[8], sk2[MODE_A ? 8 : 1];
 #pragma unroll
@@ -604,6 +628,7 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
                 mbar_wait(&s_bar, parity);
                 parity ^= 1;
             }
+            const int bnd = (staged && active) ? (int)s_bnd[tix] : 0;    // written before the barrier above
             if (active) {
                 // root weight on this half of x_i.  `half` must be a compile-time constant here as well: with a run-time index
                 // the 64 weight fetches per half become register-indexed LDC through the address-divergence unit
@@ -633,7 +658,8 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
 #undef CB2_ROOT
 #define CB2_PASS(H, G)                                                                                               \
     do {                                                                                                            \
-        if (staged) cb2_pass<true, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2); \
+        if (staged) cb2_pass<true, H, G, THREADS>(N, p, (G) == 0 ? (bnd >> 8) << 8 : ((G) == 1 ? (n + 1) << 8 : (bnd & 0xff) | ((n + 1) << 8)), \
+                                                  xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2);       \
         else        cb2_pass<false, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, tix, o2);     \
     } while (0)
 #define CB2_HALF(H)                                                                                                  \
@@ -829,7 +855,7 @@ k_l1_conv_b2_dense(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ s
 
 static size_t cb2_smem_bytes(const dagr_geom_t *g, int cap, int threads)
 {
-    return (size_t)cap * 32 + 96 * 16 + (size_t)DAGR_ELL * threads * 4 + (size_t)g->ncell * 2 + 32;
+    return (size_t)cap * 32 + 96 * 16 + (size_t)DAGR_ELL * threads * 4 + (size_t)((g->ncell + 7) & ~7) * 2 + (size_t)threads * 2 + 32;
 }
 
 template <class PT, int NCH, bool MODE_A>
