@@ -360,7 +360,9 @@ struct CB2Tile {
 // `half` and `k` are template parameters so the phase-2 weights come through the uniform datapath (LDCU.128);
 // a run-time pass index makes ptxas fetch them with register-indexed LDC, which saturates the ADU pipe.
 // s_ell[q][tid]: see the staged loop below (byte offsets of the row chunks and of the two factor-table rows).
-// Variants measured on B200 and rejected (profiles/r01_conv_b_variants.md): 15 slots x 8 channels per pass (120
+// Variants measured on B200 and rejected (profiles/r01_conv_b_variants.md, profiles/r02_conv_b_phase2_study.md; round 2: ELL entries
+// ordered by the x-slots they feed so that the outer x-slot passes skip their exact-zero edges: 1.48 -> 1.89 ms, the per-lane
+// loop bounds cost more than the skipped iterations save): 15 slots x 8 channels per pass (120
 // accumulators, 2 CTAs/SM), 15 slots x 4 channels, phase-2 weights from shared memory or half/half.
 template <bool STAGED, int half, int grp, int THREADS, class PT>
 __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *__restrict__ xa, const float *s_rows,
@@ -394,10 +396,8 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
 #define CB2_UNROLL 1                                                    // measured: 1 -> 1.49 ms, 2 -> 1.56, 3 -> 1.58, 4 -> 1.68 (registers, I-cache)
 #endif
         constexpr int kUnroll = CB2_UNROLL;
-        // n carries the staged loop bounds: bits 0..7 = first entry, bits 8..15 = end (exclusive); see the ELL staging
-        const int q_end = n >> 8;
 #pragma unroll kUnroll
-        for (int q = n & 0xff; q < q_end; q++) {
+        for (int q = 0; q <= n; q++) {
             const uint32_t ell = s_ell[q * THREADS + tix];
             const uint32_t ro = ell & 0x3fff0u, xo = (ell >> 14) & 0x1f0u, yo = (ell >> 18) & 0x3e0u;
             const float4 t0 = *reinterpret_cast<const float4 *>(rb + ro), t1 = *reinterpret_cast<const float4 *>(rb + (ro ^ 16u));
@@ -461,7 +461,8 @@ __device__ __forceinline__ int cb2_round_to_pixel(float mean, int size)
 
 // The kernel is a template over the input rows: <dagr_l1b_params_t, 2, false> is conv_block2 (16 channels = 2 staged
 // 8-channel chunks, skip + act + pool1 epilogue); <dagr_l1img_params_t, 3, true> is the image-fusion variant of
-// conv_block1.conv_block1 (1 + 16 + 2 input channels padded to 3 chunks; epilogue = BN + act, rows written back
+// conv_block1.conv_block1 (the 16 sampled image channels = 2 chunks, added to the (polarity, x, y) part the probe kernel
+// already summed; epilogue = BN + act, rows written back
 // chunk-major for conv_block2, plus the layer's skip branch BN(Linear(x0)) -> skip_out; no pooling).
 template <int THREADS>
 struct CB2Shared {
@@ -474,7 +475,8 @@ struct CB2Shared {
 
 // The per-voxel routine is a template over the input rows: <dagr_l1b_params_t, 2, false> is conv_block2 (16 channels = 2
 // staged 8-channel chunks, skip + act + pool1 epilogue); <dagr_l1img_params_t, 3, true> is the image-fusion variant of
-// conv_block1.conv_block1 (1 + 16 + 2 input channels padded to 3 chunks; epilogue = BN + act, rows written back
+// conv_block1.conv_block1 (the 16 sampled image channels = 2 chunks, added to the (polarity, x, y) part the probe kernel
+// already summed; epilogue = BN + act, rows written back
 // chunk-major for conv_block2, plus the layer's skip branch BN(Linear(x0)) -> skip_out; no pooling).
 // work list: wl_hdr[0] = number of voxels beyond this instance's staging capacity (queued in wl_ids when `defer`, otherwise
 // only counted and gathered from global memory / L2), wl_hdr[1] = pop cursor of the dense kernel
@@ -499,7 +501,6 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
     float4 *s_wy = (float4 *)(s_wx + 128);                               // [2r+1][2]   y factor
     uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [16][THREADS]  slot 0 = self loop
     uint16_t *s_sp = (uint16_t *)(s_ell + DAGR_ELL * THREADS);           // [ncell]  (dx + r) | (dy + r) << 5
-    uint16_t *s_bnd = s_sp + ((g.ncell + 7) & ~7);                          // [THREADS]  per node: n_lo | (n_lo + n_mid) << 8  (see the staging below)
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
     const int p0 = start[(int64_t)cell * g.CP], p1 = start[(int64_t)(cell + 1) * g.CP];
@@ -579,34 +580,13 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
                 jj[q] = (q < n) ? nbr[(int64_t)q * N + p] : 0;
                 cc[q] = (q < n) ? (int)off[(int64_t)q * N + p] : 0;
             }
-            // The edges are laid out by which x-slots they feed: degree-1 splines give every offset at most two adjacent
-            // non-zero x factors, so an edge left of the node (only x-slot 0 and 1) contributes exact zeros to the pass of
-            // x-slot 2 and vice versa.  Order: [slot-0 side | both / centre (incl. the self loop) | slot-2 side]; the pass of
-            // x-slot 0 then stops before the third group and the pass of x-slot 2 starts after the first (a third fewer row
-            // gathers and FMAs; skipped terms are exact zeros).
-            int cls[DAGR_ELL - 1];
-            int n_lo = 0, n_mid = 1;
 #pragma unroll
             for (int q = 0; q < DAGR_ELL - 1; q++) {
-                const uint32_t sp = s_sp[cc[q]];
-                cc[q] = (int)sp;
-                const float4 wxr = reinterpret_cast<const float4 *>(s_wx)[sp & 31u];
-                const bool has0 = wxr.x != 0.f, has2 = wxr.z != 0.f;
-                cls[q] = (has0 && !has2) ? 0 : ((has2 && !has0) ? 2 : 1);
-                if (q < n) { n_lo += cls[q] == 0; n_mid += cls[q] == 1; }
+                const int j = jj[q];
+                const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
+                s_ell[(q + 1) * THREADS + tix] = ((uint32_t)(2 * row + XA_SWZ(j)) << 4) | ((uint32_t)s_sp[cc[q]] << 18);
             }
-            int c0 = 0, c1 = n_lo, c2 = n_lo + n_mid;
-            s_ell[(c1++) * THREADS + tix] = ((uint32_t)(2 * (p + d1) + XA_SWZ(p)) << 4) | ((uint32_t)(g.r | (g.r << 5)) << 18);   // self loop
-#pragma unroll
-            for (int q = 0; q < DAGR_ELL - 1; q++) {
-                if (q < n) {
-                    const int j = jj[q];
-                    const int row = j + (j >= s2 ? d2 : (j >= s1 ? d1 : d0));
-                    const int slot = cls[q] == 0 ? c0++ : (cls[q] == 1 ? c1++ : c2++);
-                    s_ell[slot * THREADS + tix] = ((uint32_t)(2 * row + XA_SWZ(j)) << 4) | ((uint32_t)cc[q] << 18);
-                }
-            }
-            s_bnd[tix] = (uint16_t)(n_lo | ((n_lo + n_mid) << 8));
+            s_ell[tix] = ((uint32_t)(2 * (p + d1) + XA_SWZ(p)) << 4) | ((uint32_t)(g.r | (g.r << 5)) << 18);   // self loop
         }
         float2 o2[8], sk2[MODE_A ? 8 : 1];
 #pragma unroll
@@ -628,7 +608,6 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
                 mbar_wait(&s_bar, parity);
                 parity ^= 1;
             }
-            const int bnd = (staged && active) ? (int)s_bnd[tix] : 0;    // written before the barrier above
             if (active) {
                 // root weight on this half of x_i.  `half` must be a compile-time constant here as well: with a run-time index
                 // the 64 weight fetches per half become register-indexed LDC through the address-divergence unit
@@ -658,8 +637,7 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
 #undef CB2_ROOT
 #define CB2_PASS(H, G)                                                                                               \
     do {                                                                                                            \
-        if (staged) cb2_pass<true, H, G, THREADS>(N, p, (G) == 0 ? (bnd >> 8) << 8 : ((G) == 1 ? (n + 1) << 8 : (bnd & 0xff) | ((n + 1) << 8)), \
-                                                  xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2);       \
+        if (staged) cb2_pass<true, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2); \
         else        cb2_pass<false, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, tix, o2);     \
     } while (0)
 #define CB2_HALF(H)                                                                                                  \
@@ -710,13 +688,32 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
             float sk[16];
 #pragma unroll
             for (int c = 0; c < 8; c++) { sk[2 * c] = sk2[c].x; sk[2 * c + 1] = sk2[c].y; }
+            const int sw = XA_SWZ(p);
+            {
+                // the (polarity, x, y) channels of the 19-channel conv were summed by the probe kernel (they need no
+                // gather: dagr_l1_build with the event-channel weights, no BN / act) and wait in this node's xa row;
+                // their part of the skip branch Linear(x0) is three FMAs per output here
+                const float4 *pp = reinterpret_cast<const float4 *>(xa_out + (int64_t)p * 8);
+                const float4 a0 = pp[sw], a1 = pp[sw ^ 1];
+                pp = reinterpret_cast<const float4 *>(xa_out + (N + (int64_t)p) * 8);
+                const float4 a2 = pp[sw], a3 = pp[sw ^ 1];
+                const float part[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+                const uint32_t wxy = xyb[p];
+                const float f0 = feat_s[p], f1 = __ldg(g.posx0 + (wxy & 0xfff)), f2 = __ldg(g.posy0 + ((wxy >> 12) & 0xfff));
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    o[c] += part[c];
+                    sk[c] = fmaf(f0, P.skip[16][c], sk[c]);
+                    sk[c] = fmaf(f1, P.skip[17][c], sk[c]);
+                    sk[c] = fmaf(f2, P.skip[18][c], sk[c]);
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const float r = fmaf(o[c], P.scale[c], P.shift[c]);
                 o[c] = P.relu ? fmaxf(r, 0.f) : r;
                 sk[c] = fmaf(sk[c], P.sscale[c], P.sshift[c]);
             }
-            const int sw = XA_SWZ(p);
             float4 *dst = reinterpret_cast<float4 *>(xa_out + (int64_t)p * 8);
             dst[sw] = make_float4(o[0], o[1], o[2], o[3]);
             dst[sw ^ 1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -855,7 +852,7 @@ k_l1_conv_b2_dense(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ s
 
 static size_t cb2_smem_bytes(const dagr_geom_t *g, int cap, int threads)
 {
-    return (size_t)cap * 32 + 96 * 16 + (size_t)DAGR_ELL * threads * 4 + (size_t)((g->ncell + 7) & ~7) * 2 + (size_t)threads * 2 + 32;
+    return (size_t)cap * 32 + 96 * 16 + (size_t)DAGR_ELL * threads * 4 + (size_t)g->ncell * 2 + 32;
 }
 
 template <class PT, int NCH, bool MODE_A>
@@ -905,15 +902,17 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
                                                    (cudaStream_t)stream);
 }
 
-// image fusion: conv_block1.conv_block1 on the 19-channel rows x0 (chunk-major [3][N][8], chunks swizzled like xa)
-extern "C" int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const float *x0, const int32_t *nbr,
+// image fusion: the 16 image channels of conv_block1.conv_block1 (x0 chunk-major [2][N][8], chunks swizzled like xa) on top
+// of the event-channel sums the probe kernel left in xa
+extern "C" int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb, const float *feat_s,
+                                    const float *x0, const int32_t *nbr,
                                     const uint16_t *off, const dagr_l1img_params_t *p_host, float *xa, float *skipv,
                                     int32_t *wl_hdr, int32_t *wl_ids, int defer, void *stream)
 {
-    DAGR_CHECK_ARG(g && p_host, "null argument");
+    DAGR_CHECK_ARG(g && p_host && xyb && feat_s, "null argument");
     if (N <= 0) return DAGR_OK;
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
-    return cb2_launch<dagr_l1img_params_t, 3, true>(g, N, start, nullptr, nullptr, nullptr, x0, nbr, off, p_host, nullptr, 0, nullptr,
+    return cb2_launch<dagr_l1img_params_t, 2, true>(g, N, start, xyb, nullptr, feat_s, x0, nbr, off, p_host, nullptr, 0, nullptr,
                                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, xa, skipv, wl_hdr, wl_ids, defer,
                                                     (cudaStream_t)stream);
 }

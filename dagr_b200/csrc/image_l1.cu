@@ -49,37 +49,27 @@ __device__ __forceinline__ float bilin_sample(const float *__restrict__ img, int
     return acc;
 }
 
-// x0[chunk][p][8]: [pol, f0..f15, x/W, y/H, 0 x5]; the two 16-byte halves of a row are swapped when XA_SWZ(p), like xa,
-// so that the staged conv kernel (conv_l1.cu) reads both with the same row addressing
+// x0[chunk][p][8] = the 16 image channels sampled at the event (two 8-channel chunks); the two 16-byte halves of a row are
+// swapped when XA_SWZ(p), like xa, so that the staged conv kernel (conv_l1.cu) reads both with the same row addressing.
+// (polarity, x/W, y/H) -- the other three inputs of conv_block1.conv_block1 -- need no gather and are handled by the probe kernel.
 __global__ void k_l1_x0_image(const dagr_geom_t g, int64_t N, const uint32_t *__restrict__ xyb, const float *__restrict__ feat_s,
                               const float *__restrict__ img0, int h, int w, float *__restrict__ x0)
 {
-    // 4 threads per node: thread q computes image channels 4q..4q+3
+    // 4 threads per node: thread q computes image channels 4q..4q+3 = one 16-byte chunk of a row
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t p = t >> 2;
     const int q = (int)(t & 3);
     if (p >= N) return;
+    (void)feat_s;
     const uint32_t wd = xyb[p];
     const int x = wd & 0xfff, y = (wd >> 12) & 0xfff, b = wd >> 24;
     const float px = g.posx0[x], py = g.posy0[y];
     const Bilin bl = bilin_setup(px, py, b, (float)g.W, (float)g.H, g.B, h, w);
-    const int sw4 = 4 * XA_SWZ(p);
     float f[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) f[k] = bilin_sample(img0, g.B, 16, h, w, 4 * q + k, bl);
-    // channel index in the 24-wide padded row: 0 = polarity, 1..16 = image, 17 = x, 18 = y
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int ch = 1 + 4 * q + k;
-        x0[((int64_t)(ch >> 3) * N + p) * 8 + ((ch & 7) ^ sw4)] = f[k];
-    }
-    if (q == 0) {
-        x0[p * 8 + (0 ^ sw4)] = feat_s[p];
-        x0[((int64_t)2 * N + p) * 8 + (1 ^ sw4)] = px;
-        x0[((int64_t)2 * N + p) * 8 + (2 ^ sw4)] = py;
-#pragma unroll
-        for (int k = 3; k < 8; k++) x0[((int64_t)2 * N + p) * 8 + (k ^ sw4)] = 0.f;
-    }
+    float4 *dst = reinterpret_cast<float4 *>(x0 + ((int64_t)(q >> 1) * N + p) * 8);
+    dst[(q & 1) ^ XA_SWZ(p)] = make_float4(f[0], f[1], f[2], f[3]);
 }
 
 extern "C" int dagr_l1_x0_image(const dagr_geom_t *g, int64_t N, const uint32_t *xyb, const float *feat_s, const float *img0,

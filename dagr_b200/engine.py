@@ -232,11 +232,20 @@ class Engine:
             _fill(pb.skip, cb.lin.mlp.weight.detach().cpu().t())            # [3,16]
             pk["l1a"] = pa
         else:
+            # input channels of the layer: [polarity, 16 image samples, x, y] (net.py:117-124).  The image channels go to the
+            # TMA-staged conv (rows 0..15 of the padded 24), the three event channels to the probe kernel (they need no gather)
+            order = list(range(1, 17)) + [0, 17, 18]
             pi = _lib.L1ImgParams()
-            w = torch.zeros(15, 24, 16); w[:, :19] = ca.conv.weight.detach().cpu().float()[slots]
-            r = torch.zeros(24, 16); r[:19] = ca.conv.lin.weight.detach().cpu().float().t()
-            k = torch.zeros(24, 16); k[:19] = cb.lin.mlp.weight.detach().cpu().float().t()
+            w = torch.zeros(15, 24, 16); w[:, :19] = ca.conv.weight.detach().cpu().float()[slots][:, order]
+            r = torch.zeros(24, 16); r[:19] = ca.conv.lin.weight.detach().cpu().float().t()[order]
+            k = torch.zeros(24, 16); k[:19] = cb.lin.mlp.weight.detach().cpu().float().t()[order]
             _fill(pi.w, w); _fill(pi.root, r); _fill(pi.skip, k)
+            pe = _lib.L1AParams()                            # event-channel part: plain sums (BN / act happen after the image part)
+            _fill(pe.w, ca.conv.weight.detach().cpu().float()[slots][:, [0, 17, 18]])
+            _fill(pe.root, ca.conv.lin.weight.detach().cpu().float().t()[[0, 17, 18]])
+            _fill(pe.scale, torch.ones(16)); _fill(pe.shift, torch.zeros(16))
+            pe.relu = 0
+            pk["l1a_img"] = pe
             s, b = _fold_bn(ca.norm); _fill(pi.scale, s); _fill(pi.shift, b)
             s, b = _fold_bn(cb.norm_skip); _fill(pi.sscale, s); _fill(pi.sshift, b)
             pi.relu = 1
@@ -544,18 +553,20 @@ class Engine:
                       _lib.ptr(ws["feat_s"]), _lib.ptr(flags), st)
         use_image = image_feats is not None
         if use_image:
-            # adjacency only; conv_block1 runs on [polarity, 16 image samples, x, y] (net.py:117-126)
+            # adjacency + the (polarity, x, y) part of conv_block1.conv_block1, which runs on [polarity, 16 image samples, x, y]
+            # (net.py:117-126); the image channels follow in dagr_l1_conv_a_image
             self._run("l1_build", lib.dagr_l1_build, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["ti"]), _lib.ptr(ws["xyb"]),
-                      _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), None, _lib.ptr(flags), 0, _lib.ptr(nbr), _lib.ptr(off),
+                      _lib.ptr(ws["feat_s"]), _lib.ptr(geom.d_tab1), C.byref(pk["l1a_img"]), _lib.ptr(flags), 0, _lib.ptr(nbr), _lib.ptr(off),
                       _lib.ptr(cellmask), _lib.ptr(ws["xa"]), _lib.ptr(wl_hdr), _lib.ptr(self._zs(ws, "wl_build", torch.int32)), defer[0], st)
             if image_event is not None:                       # stage 1 of the image branch ran on a side stream next to sort + probe
                 torch.cuda.current_stream().wait_event(image_event[0])
             f0 = image_feats[0]
-            x0 = self._buf(ws, "x0img", (3 * max(N, 1) * 8,), torch.float32, dev)
+            x0 = self._buf(ws, "x0img", (2 * max(N, 1) * 8,), torch.float32, dev)
             skipv = self._buf(ws, "skipv", (max(N, 1), 16), torch.float32, dev)
             self._run("l1_x0_image", lib.dagr_l1_x0_image, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(f0),
                       int(f0.shape[2]), int(f0.shape[3]), _lib.ptr(x0), st)
-            self._run("l1_conv_a_image", lib.dagr_l1_conv_a_image, g, N, _lib.ptr(ws["start"]), _lib.ptr(x0), _lib.ptr(nbr), _lib.ptr(off),
+            self._run("l1_conv_a_image", lib.dagr_l1_conv_a_image, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]),
+                      _lib.ptr(x0), _lib.ptr(nbr), _lib.ptr(off),
                       C.byref(pk["l1img"]), _lib.ptr(ws["xa"]), _lib.ptr(skipv), _lib.ptr(wl_hdr[2:]),
                       _lib.ptr(self._zs(ws, "wl_conv_a", torch.int32)), defer[1], st)
         elif self.fused_build or stream_state is not None:

@@ -173,10 +173,14 @@ typedef struct {
     int32_t relu;
 } dagr_l1img_params_t;
 
-/* conv_block1.conv_block1 on 19 input channels (x0 chunk-major [3][N][8] from dagr_l1_x0_image) -> xa (half-major
- * [2][N][8]) and the layer's skip branch skipv f32[N,16] = BN(Linear(x0)) consumed by dagr_l1_conv_b_pool_voxel(skip_pre).
- * Same one-CTA-per-voxel, TMA-staged kernel as conv_block2 (template instance with 3 input chunks). */
-int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const float *x0, const int32_t *nbr,
+/* conv_block1.conv_block1 on 19 input channels, image fusion.  The (polarity, x, y) channels need no gather: dagr_l1_build runs
+ * first with their weights (rows 0, 17, 18 of the conv, scale 1 / shift 0 / relu 0) and leaves their sums in xa; this call adds
+ * the 16 sampled image channels (x0 chunk-major [2][N][8] from dagr_l1_x0_image; rows 0..15 of p_host->w / root / skip), applies
+ * BN + act -> xa (half-major [2][N][8]) and writes the layer's skip branch skipv f32[N,16] = BN(Linear(x0)) (rows 16..18 of
+ * p_host->skip = polarity, x, y) consumed by dagr_l1_conv_b_pool_voxel(skip_pre).  Same one-CTA-per-voxel, TMA-staged kernel as
+ * conv_block2. */
+int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb, const float *feat_s,
+                         const float *x0, const int32_t *nbr,
                          const uint16_t *off, const dagr_l1img_params_t *p_host /* passed by value to the kernel (26 KB) */,
                          float *xa, float *skipv,
                          int32_t *wl_hdr, int32_t *wl_ids, int defer /* dense-voxel work list, see dagr_l1_conv_b_pool_voxel */,

@@ -795,3 +795,29 @@ def test_no_events_returns_the_image_only_head_like_the_reference():
     assert_close(dec.cpu(), want, tol=1e-6, what="no_events decoded")
     dets = model(data.clone().cuda())[0]
     assert len(dets) == B
+
+
+@pytest.mark.parametrize("use_image", [False, True])
+def test_reloading_weights_after_graph_capture_takes_effect(use_image):
+    """the coarse stack (and the image branch) are replayed as CUDA graphs that hold pointers to packed weights: after
+    load_state_dict the next forward must use the NEW weights (graph cache keyed on a pack generation, image graphs dropped)."""
+    from dagr_b200.data import format_data, synth_batch
+    W, H, B = 240, 180, 2
+    kw = dict(use_image=True, img_net="resnet18") if use_image else {}
+    model_a, _ = make_model("n", H, W, seed=0, batch_size=B, **kw)
+    model_b, _ = make_model("n", H, W, seed=5, batch_size=B, **kw)
+    model_a.cuda(); model_b.cuda()
+    data = format_data(synth_batch(B, 4000, W, H, seed=9, with_image=use_image).clone()).cuda()
+    for _ in range(4):                                         # eager, warm, capture, replay
+        out_a = model_a.forward_decoded(data.clone()).clone()
+    want_b = model_b.forward_decoded(data.clone()).clone()
+    torch.cuda.synchronize()
+    assert not torch.equal(out_a, want_b)
+    model_a.load_state_dict(model_b.state_dict())
+    for k in range(3):
+        got = model_a.forward_decoded(data.clone()).clone()
+        torch.cuda.synchronize()
+        if use_image:                                          # cuDNN may pick another algorithm for the re-captured branch
+            assert_close(got, want_b, tol=1e-4, what="decoded after reload (image)")
+        else:
+            assert torch.equal(got, want_b), f"forward {k} after load_state_dict still uses old weights"
