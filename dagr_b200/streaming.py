@@ -185,6 +185,10 @@ def stream_benchmark(dev, size="l", width=640, height=480, rate_ev_s=1_000_000, 
     nchunks = len(bounds) - 1
     lat, dev_ms, evs = [], [], []
     warm = int(window_us / chunk_us) + 20                                # fill the live window first (+ graph capture)
+    import gc
+    gc_was = gc.isenabled()
+    gc.collect()
+    gc.disable()                                                         # a collector pause inside a 1 ms chunk period is a latency spike
     for k in range(nchunks):
         a, b = int(bounds[k]), int(bounds[k + 1])
         t_end = (k + 1) * chunk_us
@@ -200,6 +204,8 @@ def stream_benchmark(dev, size="l", width=640, height=480, rate_ev_s=1_000_000, 
             evs.append(b - a)
         else:
             det.push(x[a:b], y[a:b], t[a:b], p[a:b], t_end)
+    if gc_was:
+        gc.enable()
     st = det.window_state
     lat_s, dev_s = sorted(lat), sorted(dev_ms)
     q = lambda v, f: v[min(len(v) - 1, int(f * len(v)))]
@@ -214,4 +220,5 @@ def stream_benchmark(dev, size="l", width=640, height=480, rate_ev_s=1_000_000, 
                 note="one stream on one GPU; every chunk: H2D of the chunk from pinned memory, eviction by watermark + append into the "
                      "device ring, full forward over the live window, NMS, D2H of the detections -- one CUDA graph replay; latency = host "
                      "wall clock from submit() to the detections being readable on the host, chunks submitted back to back "
-                     "(sustained_mev_s = events / busy time: how much faster than the 1 Mevents/s feed the loop runs)")
+                     "(sustained_mev_s = events / busy time: how much faster than the 1 Mevents/s feed the loop runs); Python's cyclic garbage "
+                     "collector is paused during the timed loop")

@@ -147,7 +147,8 @@ int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *start, const i
                                  OR-ed into its previous content; 0 = everything */,
                   int32_t *nbr, uint16_t *off, uint32_t *cellmask, float *xa,
                   int32_t *wl_hdr /* i32[2] ZERO on entry, or NULL: [0] counts the voxels whose 3x3 neighbourhood exceeds the
-                                     per-voxel kernel's staging capacity (2048 records; moving edges), [1] is the dense kernel's cursor */,
+                                     per-voxel kernel's staging capacity (defer = 1: 2048 records; defer = 0: the lean launch with
+                                     1536 records and five CTAs per SM), [1] is the dense kernel's cursor */,
                   int32_t *wl_ids /* i32[cells] or NULL: ids of those voxels when `defer` */,
                   int defer /* 1: such voxels are queued and processed by a second, persistent launch with a 12288-record staging
                                buffer; 0: they are only counted and probe global memory (slow, exact) -- a caller can watch
