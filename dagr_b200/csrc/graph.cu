@@ -127,6 +127,32 @@ extern "C" int dagr_denormalize_pos(const float *pos, int64_t N, int W, int H, i
     return DAGR_OK;
 }
 
+// The whole input conversion of DAGR.forward in one pass: denormalize_pos (above), batch int64 -> int32 (ev_tgn.py:57
+// passes events.batch.int()) and the polarity column of x as a dense fp32 vector.
+__global__ void k_prepare_events(const float *__restrict__ pos, const int64_t *__restrict__ batch64, const float *__restrict__ x, int ldx,
+                                 int64_t N, float W, float H, float T, int32_t *__restrict__ pos_i, int32_t *__restrict__ batch_i,
+                                 float *__restrict__ feat)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    pos_i[3 * i + 0] = (int)__fadd_rn(__fmul_rn(W, pos[3 * i + 0]), 1e-3f);
+    pos_i[3 * i + 1] = (int)__fadd_rn(__fmul_rn(H, pos[3 * i + 1]), 1e-3f);
+    pos_i[3 * i + 2] = (int)__fadd_rn(__fmul_rn(T, pos[3 * i + 2]), 1e-3f);
+    batch_i[i] = (int32_t)batch64[i];
+    feat[i] = x[i * ldx];
+}
+
+extern "C" int dagr_prepare_events(const float *pos, const int64_t *batch, const float *x, int ldx, int64_t N, int W, int H, int T,
+                                   int32_t *pos_i32, int32_t *batch_i32, float *feat, void *stream)
+{
+    if (N <= 0) return DAGR_OK;
+    DAGR_CHECK_ARG(pos && batch && x && pos_i32 && batch_i32 && feat && ldx >= 1, "bad argument");
+    k_prepare_events<<<dagr_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(pos, batch, x, ldx, N, (float)W, (float)H, (float)T, pos_i32,
+                                                                          batch_i32, feat);
+    DAGR_CHECK_LAUNCH();
+    return DAGR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // sort
 // ------------------------------------------------------------------------------------------------

@@ -180,12 +180,27 @@ class DAGR(YOLOX):
         if getattr(x, "batch", None) is None:
             x.batch = torch.zeros(len(x.pos), dtype=torch.long, device=dev)
         N = int(x.pos.shape[0])
+        lib = self.engine.lib
+        xf = x.x
+        fused = (not (hasattr(x, "pos_denorm") and x.pos_denorm is not None) and N > 0 and x.pos.dtype == torch.float32
+                 and x.pos.is_contiguous() and x.batch.dtype == torch.int64 and x.batch.is_contiguous() and xf.dtype == torch.float32
+                 and xf.dim() in (1, 2) and xf.stride(-1) == 1 and (xf.dim() == 1 or xf.stride(0) == xf.shape[1]))
+        if fused:
+            # one launch: denormalize_pos + batch.int() + polarity column (no at:: cast / copy kernels on the call path)
+            pos_i = torch.empty((N, 3), dtype=torch.int32, device=dev)
+            batch_i = torch.empty(N, dtype=torch.int32, device=dev)
+            feat = torch.empty(N, dtype=torch.float32, device=dev)
+            ldx = 1 if xf.dim() == 1 else int(xf.shape[1])
+            _lib.check(lib.dagr_prepare_events(_lib.ptr(x.pos), _lib.ptr(x.batch), _lib.ptr(xf), ldx, N, W, H, T, _lib.ptr(pos_i),
+                                               _lib.ptr(batch_i), _lib.ptr(feat), _lib.stream_ptr()), "prepare_events")
+            self.engine.launches += 1
+            return batch_i, pos_i, feat, W, H
         if hasattr(x, "pos_denorm") and x.pos_denorm is not None:               # ev_tgn.py:12-13
             pos_i = x.pos_denorm.int().contiguous()
         else:
             pos_f = x.pos.float().contiguous()
             pos_i = torch.empty((N, 3), dtype=torch.int32, device=dev)
-            _lib.check(self.engine.lib.dagr_denormalize_pos(_lib.ptr(pos_f), N, W, H, T, _lib.ptr(pos_i), _lib.stream_ptr()),
+            _lib.check(lib.dagr_denormalize_pos(_lib.ptr(pos_f), N, W, H, T, _lib.ptr(pos_i), _lib.stream_ptr()),
                        "denormalize_pos")
         batch_i = x.batch.int().contiguous()
         feat = x.x.float().reshape(N, -1)[:, 0].contiguous() if N > 0 else torch.zeros(0, device=dev)

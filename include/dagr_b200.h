@@ -83,6 +83,11 @@ int dagr_pool_workspace_bytes(int64_t parent_cells, int channels, dagr_pool_ws_t
  * ------------------------------------------------------------------------------------------- */
 int dagr_denormalize_pos(const float *pos /*[N,3]*/, int64_t N, int W, int H, int T,
                          int32_t *pos_i32 /*[N,3]*/, void *stream);
+/* the input conversion of one forward in a single launch: denormalize_pos + `events.batch.int()` (ev_tgn.py:57) + the
+ * polarity column x[:, 0] (row stride ldx) as a dense vector */
+int dagr_prepare_events(const float *pos /*[N,3]*/, const int64_t *batch /*[N]*/, const float *x /*[N,ldx]*/, int ldx, int64_t N,
+                        int W, int H, int T, int32_t *pos_i32 /*[N,3]*/, int32_t *batch_i32 /*[N]*/, float *feat /*[N]*/,
+                        void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a2-a4  radius graph.  Replaces ev_graph_cuda.insert_in_queue_cuda + fill_edges_cuda
