@@ -75,3 +75,50 @@ def test_oracle_equals_the_references_async_helpers():
     hom = t("hom")
     assert torch.equal(hom[:, :-1], pos) and bool((hom[:, -1] == 1).all())
     assert_close(t("from_hom"), R.scatter_mean(pos, cl, int(cl.max()) + 1), tol=1e-6, what="from_hom vs scatter_mean")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The arithmetic inside the absent third-party packages (torch_spline_conv, torch_cluster, torch_scatter) has no fixture
+# from the packages themselves; the oracle's restatements are cross-checked against INDEPENDENT implementations of the same
+# published definitions (scipy B-splines, numpy / pandas group-bys) so that they are not only self-consistent.
+# ------------------------------------------------------------------------------------------------------------------
+def test_spline_basis_matches_scipy_bspline_design_matrix():
+    """degree-1 open B-spline basis on kernel_size uniform knots == scipy.interpolate.BSpline.design_matrix (k = 1)."""
+    from scipy.interpolate import BSpline
+    from oracle import ref_ops as R
+    ks = 5
+    g = torch.Generator().manual_seed(2)
+    pseudo = torch.rand(4000, 2, generator=g, dtype=torch.float64)
+    pseudo[:8] = torch.tensor([[0.0, 0.0], [0.25, 0.5], [0.5, 0.5], [0.999999, 0.3], [0.125, 0.875], [0.75, 0.0], [0.3, 0.7], [0.6, 0.1]])
+    basis, index = R.spline_basis(pseudo, ks, True, 1)
+    dense = torch.zeros(len(pseudo), ks * ks, dtype=torch.float64)
+    dense.scatter_add_(1, index, basis)
+    # open spline, degree 1: ks hat functions on the uniform knots 0, 1/(ks-1), ..., 1 (clamped ends)
+    t = np.concatenate([[0.0], np.linspace(0.0, 1.0, ks), [1.0]])
+    bx = BSpline.design_matrix(pseudo[:, 0].numpy(), t, 1).toarray()          # [E, ks]
+    by = BSpline.design_matrix(pseudo[:, 1].numpy(), t, 1).toarray()
+    want = (by[:, :, None] * bx[:, None, :]).reshape(len(pseudo), ks * ks)    # slot = kx + ks * ky
+    assert np.abs(dense.numpy() - want).max() < 1e-12
+    assert np.allclose(basis.sum(1).numpy(), 1.0)
+
+
+def test_grid_cluster_and_scatter_match_numpy_and_pandas():
+    import pandas as pd
+    from oracle import ref_ops as R
+    g = torch.Generator().manual_seed(4)
+    n, B = 5000, 3
+    pos = torch.rand(n, 3, generator=g)
+    batch = torch.randint(0, B, (n,), generator=g)
+    size = torch.tensor([1.0 / 56, 1.0 / 40, 1.0, 1.0])
+    pos4 = torch.cat([pos, batch.float().view(-1, 1)], 1)
+    c = R.grid_cluster(pos4, size, torch.zeros(4), torch.tensor([0.9999999, 0.9999999, 0.9999999, B - 1.0]))
+    # voxel id = x-cell + 56 * (y-cell + 40 * (t-cell + 1 * batch)), cells by fp32 division and truncation
+    cell = np.trunc(pos4.numpy() / size.numpy()).astype(np.int64)
+    want = cell[:, 0] + 56 * (cell[:, 1] + 40 * (cell[:, 2] + 1 * cell[:, 3]))
+    assert np.array_equal(c.numpy(), want)
+    uniq, cl, _, _ = R.consecutive_cluster(c)
+    x = torch.randn(n, 7, generator=g)
+    df = pd.DataFrame(x.numpy()).assign(cl=cl.numpy())
+    assert np.array_equal(R.scatter_max(x, cl, len(uniq)).numpy(), df.groupby("cl").max().to_numpy().astype(np.float32))
+    mean = df.groupby("cl").mean().to_numpy()
+    assert np.abs(R.scatter_mean(x, cl, len(uniq)).numpy() - mean).max() < 1e-5
