@@ -220,9 +220,10 @@ k_grid_conv_sk(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int3
     float *A = smem_f;                                         // [26][Cin][CPB]
     // [SK_WARPS][CPB][Cout]; aliases A when there is a single 64-wide output tile (A is dead after phase 2)
     float *part = (Cout <= 64) ? A : A + (size_t)SK_SLOTS * Cin * CPB;
-    __shared__ int s_src[CPB][8];
-    __shared__ float s_w[CPB][8][4];
-    __shared__ unsigned char s_slot[CPB][8][4];
+    // edge tables with the voxel index innermost: phase 1 runs with the voxel index fastest across lanes
+    __shared__ int s_src[8][CPB];
+    __shared__ float s_w[8][4][CPB];
+    __shared__ unsigned char s_slot[8][4][CPB];
     __shared__ int s_ne[CPB];
     __shared__ unsigned int s_used;
     const int cells = gr.B * gr.ny * gr.nx;
@@ -251,37 +252,44 @@ k_grid_conv_sk(const dagr_grid_t gr, const int32_t *__restrict__ cnt, const int3
                     float w[4]; int slot[4];
                     spline_basis2(ax, ay, 5, w, slot);
                     const int e = bit < 4 ? bit : bit - 1;              // dense edge index 0..7
-                    s_src[j][e] = src;
+                    s_src[e][j] = src;
                     unsigned int used = 0;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) { s_w[j][e][q] = w[q]; s_slot[j][e][q] = (unsigned char)slot[q]; if (w[q] != 0.f) used |= 1u << slot[q]; }
+                    for (int q = 0; q < 4; q++) { s_w[e][q][j] = w[q]; s_slot[e][q][j] = (unsigned char)slot[q]; if (w[q] != 0.f) used |= 1u << slot[q]; }
                     atomicOr(&s_used, used);
                     goto table_done;
                 }
             }
-            { const int e = bit < 4 ? bit : bit - 1; s_src[j][e] = -1; }
+            { const int e = bit < 4 ? bit : bit - 1; s_src[e][j] = -1; }
         } else {
             const int e = bit < 4 ? bit : bit - 1;
-            if (bit != 4) s_src[j][e] = -1;
+            if (bit != 4) s_src[e][j] = -1;
         }
     }
 table_done:
     __syncthreads();
     // ---- phase 1: A[k][c][j] --------------------------------------------------------------------------------
+    // the voxel index j runs fastest across the lanes: the read-modify-writes of A then touch CPB consecutive floats per
+    // channel (conflict free for any mix of slots, since Cin*CPB is a multiple of 32 banks); with the channel fastest every
+    // access of a warp fell on two banks (stride CPB floats: 16-way conflicts at CPB = 16).  The source rows sit in L2 / L1.
     for (int i = tid; i < CPB * Cin; i += blockDim.x) {
-        const int j = i / Cin, c = i % Cin;
+        const int j = i % CPB, c = i / CPB;
         const int cell = cell0 + j;
         if (cell >= cells || cnt[cell] <= 0) continue;
         A[((size_t)25 * Cin + c) * CPB + j] = xin[(int64_t)cell * ldin + c];          // root "slot"
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {                                                 // all gathers in flight before the updates
+            const int src = s_src[e][j];
+            v[e] = (src >= 0) ? xin[(int64_t)src * ldin + c] : 0.f;
+        }
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int src = s_src[j][e];
-            if (src < 0) continue;
-            const float v = xin[(int64_t)src * ldin + c];
+            if (s_src[e][j] < 0) continue;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                float *a = A + ((size_t)s_slot[j][e][q] * Cin + c) * CPB + j;
-                *a = fmaf(s_w[j][e][q], v, *a);
+                float *a = A + ((size_t)s_slot[e][q][j] * Cin + c) * CPB + j;
+                *a = fmaf(s_w[e][q][j], v[e], *a);
             }
         }
     }
