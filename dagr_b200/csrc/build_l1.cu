@@ -226,11 +226,11 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
     const int TWmax = g.CW + 2 * g.r, THmax = g.CH + 2 * g.r, TPmax = TWmax * THmax;
     int2 *s_ti = (int2 *)smem_raw;                                      // [CAP]
     float *s_feat = (float *)(s_ti + CAP);                              // [CAP]
-    uint32_t *s_pbin = (uint32_t *)(s_feat + CAP);                      // [TP]  pos << 8 | visible count
+    uint16_t *s_rng = (uint16_t *)(s_feat + CAP);                       // [TP][BL_NB]  lo | hi << 8   (16-byte aligned: CAP % 4 == 0)
+    uint32_t *s_pbin = (uint32_t *)(s_rng + TPmax * BL_NB);             // [TP]  pos << 8 | visible count
     float *s_posx = (float *)(s_pbin + TPmax);                          // [TWmax]
     float *s_posy = s_posx + TWmax;                                     // [THmax]
-    uint16_t *s_rng = (uint16_t *)(s_posy + THmax);                     // [TP][BL_NB]  lo | hi << 8
-    short *s_sp = (short *)(s_rng + TPmax * BL_NB);                     // [ncell]  dx | dy << 8
+    short *s_sp = (short *)(s_posy + THmax);                     // [ncell]  dx | dy << 8
     short *s_sp2 = s_sp + g.ncell;                                      // [ncell]  dy*TW + dx
     uint16_t *s_order = (uint16_t *)(s_sp2 + g.ncell);                  // [THREADS]
     uint32_t *s_acc = (uint32_t *)(smem_raw + bl_acc_offset(g, CAP, THREADS));   // [K-1][THREADS]  record << 10 | cell
@@ -333,10 +333,6 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
     bool bucketed = staged && (T.smax - sbase) < BL_NB && (flags == nullptr || flags[0] == 0);   // block-uniform
     const bool use_rings = TW <= 32 && TH <= 32 && g.r <= 8;            // block-uniform (a ring = 8d <= 64 mask bits)
     for (int pass = 0; pass < 2; pass++) {
-        if (use_rings) {
-            for (int i = threadIdx.x; i < BL_NB * (TH + TW); i += blockDim.x) s_occ_r[i] = 0u;   // s_occ_c follows s_occ_r
-            __syncthreads();
-        }
         for (int i = threadIdx.x; i < TP; i += blockDim.x) {
             const uint32_t pb = s_pbin[i];
             const int vis = pb & 0xff, base = pb >> 8;
@@ -357,15 +353,38 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
 #pragma unroll
                 for (int q = 1; q <= BL_NB; q++) cum[q] = (unsigned char)vis;
             }
-            const int oty = i / TW, otx = i % TW;
+            // the eight (lo | hi << 8) ranges of a pixel are one 16-byte store (eight 2-byte stores at a 16-byte lane stride
+            // cost four wavefronts each)
+            static_assert(BL_NB == 8, "one uint4 per pixel");
+            uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < BL_NB; e++) {
-                const int lo = cum[e > 0 ? e - 1 : 0], hi = cum[e + 1];
-                s_rng[i * BL_NB + e] = (uint16_t)(lo | (hi << 8));
-                if (use_rings && hi > lo) {                              // occupancy bitmasks for the ring walk
-                    atomicOr(&s_occ_r[e * TH + oty], 1u << otx);
-                    atomicOr(&s_occ_c[e * TW + otx], 1u << oty);
+            for (int e = 0; e < BL_NB; e += 2) {
+                const uint32_t r0 = (uint32_t)cum[e > 0 ? e - 1 : 0] | ((uint32_t)cum[e + 1] << 8);
+                const uint32_t r1 = (uint32_t)cum[e] | ((uint32_t)cum[e + 2] << 8);
+                w[e >> 1] = r0 | (r1 << 16);
+            }
+            reinterpret_cast<uint4 *>(s_rng)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncthreads();
+        if (use_rings) {
+            // occupancy bitmasks for the ring walk: one thread per (bucket, tile row) / (bucket, tile column) word scans its
+            // pixels -- no atomics (one atomicOr per pixel and bucket serialised on the row word: 6x the ideal wavefronts)
+            for (int idx = threadIdx.x; idx < BL_NB * (TH + TW); idx += blockDim.x) {
+                uint32_t m = 0;
+                if (idx < BL_NB * TH) {
+                    const int e = idx / TH, row = idx % TH;
+                    for (int x = 0; x < TW; x++) {
+                        const uint32_t rg = s_rng[(row * TW + x) * BL_NB + e];
+                        m |= ((rg >> 8) > (rg & 0xff)) ? (1u << x) : 0u;
+                    }
+                } else {
+                    const int i2 = idx - BL_NB * TH, e = i2 / TW, col = i2 % TW;
+                    for (int y = 0; y < TH; y++) {
+                        const uint32_t rg = s_rng[(y * TW + col) * BL_NB + e];
+                        m |= ((rg >> 8) > (rg & 0xff)) ? (1u << y) : 0u;
+                    }
                 }
+                s_occ_r[idx] = m;                                        // s_occ_c follows s_occ_r: [BL_NB][TH] then [BL_NB][TW]
             }
         }
         __syncthreads();

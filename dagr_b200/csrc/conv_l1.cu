@@ -366,7 +366,7 @@ struct CB2Tile {
 // accumulators, 2 CTAs/SM), 15 slots x 4 channels, phase-2 weights from shared memory or half/half.
 template <bool STAGED, int half, int grp, int THREADS, class PT>
 __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *__restrict__ xa, const float *s_rows,
-                                         const float *s_wx, const float4 *s_wy, const uint32_t *s_ell, const uint16_t *s_sp,
+                                         const float *s_wx, const float4 *s_wy, const float *s_wy4, const uint32_t *s_ell, const uint16_t *s_sp,
                                          const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
                                          const PT &P, int own_row, int r, int tix, float2 o2[8])
 {
@@ -391,7 +391,10 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
         // the self loop.  Every instruction costs an issue slot (one per cycle and SMSP) and the loop is issue bound, so
         // the 8 shifts/masks/adds this saves per edge and pass were worth 9 % of the kernel (profiles/r01_ubench_pipes.txt).
         const char *rb = reinterpret_cast<const char *>(s_rows);
-        const char *wxb = reinterpret_cast<const char *>(s_wx) + 4 * grp, *wyb = reinterpret_cast<const char *>(s_wy);
+        // factor tables, laid out so that a warp's lookups do not collide: wx [3 x-slots][32 offsets] (stride 4 B: lanes with the
+        // same offset broadcast, different offsets hit different banks), wy[0..3] as one float4 per offset (16 B stride), wy[4] apart
+        const char *wxb = reinterpret_cast<const char *>(s_wx) + 128 * grp, *wyb = reinterpret_cast<const char *>(s_wy);
+        const char *wy4b = reinterpret_cast<const char *>(s_wy4);
 #ifndef CB2_UNROLL
 #define CB2_UNROLL 1                                                    // measured: 1 -> 1.49 ms, 2 -> 1.56, 3 -> 1.58, 4 -> 1.68 (registers, I-cache)
 #endif
@@ -399,11 +402,11 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
 #pragma unroll kUnroll
         for (int q = 0; q <= n; q++) {
             const uint32_t ell = s_ell[q * THREADS + tix];
-            const uint32_t ro = ell & 0x3fff0u, xo = (ell >> 14) & 0x1f0u, yo = (ell >> 18) & 0x3e0u;
+            const uint32_t ro = ell & 0x3fff0u, xo = (ell >> 16) & 0x7cu, yo = (ell >> 19) & 0x1f0u;
             const float4 t0 = *reinterpret_cast<const float4 *>(rb + ro), t1 = *reinterpret_cast<const float4 *>(rb + (ro ^ 16u));
             const float wx = *reinterpret_cast<const float *>(wxb + xo);
             const float4 wya = *reinterpret_cast<const float4 *>(wyb + yo);
-            const float wy4 = *reinterpret_cast<const float *>(wyb + yo + 16);
+            const float wy4 = *reinterpret_cast<const float *>(wy4b + (yo >> 2));
             CB2_EDGE_FMA();
         }
     } else {
@@ -419,9 +422,9 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
             const int sw = XA_SWZ(row);
             const float4 *src = reinterpret_cast<const float4 *>(xa + ((int64_t)half * N + row) * 8);
             const float4 t0 = src[sw], t1 = src[sw ^ 1];
-            const float wx = s_wx[dxi * 4 + grp];
-            const float4 wya = s_wy[2 * dyi];
-            const float wy4 = s_wy[2 * dyi + 1].x;
+            const float wx = s_wx[grp * 32 + dxi];
+            const float4 wya = s_wy[dyi];
+            const float wy4 = s_wy4[dyi];
             CB2_EDGE_FMA();
         }
     }
@@ -497,9 +500,10 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
     auto &s_sum = S.sum;
     auto &s_tm = S.tm;
     float *s_rows = (float *)smem_raw;                                   // [CAP][8]   one channel half of the 3 runs
-    float *s_wx = s_rows + (size_t)CAP * 8;                              // [2r+1][4]   x factor of the slot weights
-    float4 *s_wy = (float4 *)(s_wx + 128);                               // [2r+1][2]   y factor
-    uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [16][THREADS]  slot 0 = self loop
+    float *s_wx = s_rows + (size_t)CAP * 8;                              // [3][32]   x factor of the slot weights, per x-slot
+    float4 *s_wy = (float4 *)(s_wx + 128);                               // [32]      y factors 0..3
+    float *s_wy4 = (float *)(s_wy + 32);                                 // [32]      y factor 4
+    uint32_t *s_ell = (uint32_t *)(s_wy + 64);                           // [16][THREADS]  slot 0 = self loop (384 floats of tables before it)
     uint16_t *s_sp = (uint16_t *)(s_ell + DAGR_ELL * THREADS);           // [ncell]  (dx + r) | (dy + r) << 5
     const int per = g.ny1 * g.nx1;
     const int b = cell / per, rem = cell % per, cy = rem / g.nx1, cx = rem % g.nx1;
@@ -528,9 +532,10 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
         }
     }
     for (int i = threadIdx.x; i < 2 * g.r + 1; i += blockDim.x) {
-        reinterpret_cast<float4 *>(s_wx)[i] = __ldg(reinterpret_cast<const float4 *>(g.tabx) + i);
-        s_wy[2 * i] = __ldg(reinterpret_cast<const float4 *>(g.taby) + 2 * i);
-        s_wy[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(g.taby) + 2 * i + 1);
+        const float4 tx = __ldg(reinterpret_cast<const float4 *>(g.tabx) + i);
+        s_wx[i] = tx.x; s_wx[32 + i] = tx.y; s_wx[64 + i] = tx.z;
+        s_wy[i] = __ldg(reinterpret_cast<const float4 *>(g.taby) + 2 * i);
+        s_wy4[i] = __ldg(g.taby + 8 * i + 4);
     }
     for (int i = threadIdx.x; i < g.ncell; i += blockDim.x)
         s_sp[i] = (uint16_t)(((int)g.spiral[2 * i] + g.r) | (((int)g.spiral[2 * i + 1] + g.r) << 5));
@@ -637,8 +642,8 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
 #undef CB2_ROOT
 #define CB2_PASS(H, G)                                                                                               \
     do {                                                                                                            \
-        if (staged) cb2_pass<true, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2); \
-        else        cb2_pass<false, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_ell, s_sp, nbr, off, P, 0, g.r, tix, o2);     \
+        if (staged) cb2_pass<true, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_wy4, s_ell, s_sp, nbr, off, P, p + d1, g.r, tix, o2); \
+        else        cb2_pass<false, H, G, THREADS>(N, p, n, xa, s_rows, s_wx, s_wy, s_wy4, s_ell, s_sp, nbr, off, P, 0, g.r, tix, o2);     \
     } while (0)
 #define CB2_HALF(H)                                                                                                  \
     do {                                                                                                            \
