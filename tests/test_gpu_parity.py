@@ -206,6 +206,7 @@ def test_graph_vs_reference_cuda_kernels():
 
 # ---------------------------------------------------------------------------------------------
 FWD_CASES = [
+    (1280, 720, 1, 60000, "clustered", "n", "dsec"),          # r = 13 px: cell walk instead of the ring walk (tiles wider than 32 px)
     (240, 180, 1, 6000, "uniform", "n", "ncaltech101"),
     (320, 215, 2, 12000, "clustered", "s", "dsec"),
     (640, 480, 2, 25000, "uniform", "s", "dsec"),
