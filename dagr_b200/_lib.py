@@ -64,7 +64,7 @@ class L1ImgParams(C.Structure):
 class L1BParams(C.Structure):
     _fields_ = [("w", f32 * (KU * 16 * 16)), ("root", f32 * (16 * 16)), ("skip", f32 * (3 * 16)),
                 ("scale", f32 * 16), ("shift", f32 * 16), ("sscale", f32 * 16), ("sshift", f32 * 16),
-                ("relu", i32), ("xs", i32 * 3), ("ys", i32 * 5), ("den_x", f32), ("den_y", f32)]
+                ("relu", i32), ("pool_mean", i32), ("xs", i32 * 3), ("ys", i32 * 5), ("den_x", f32), ("den_y", f32)]
 
 
 _SIGS = {

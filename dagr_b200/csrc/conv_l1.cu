@@ -288,6 +288,7 @@ extern "C" int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32
                                    const dagr_l1b_params_t *p_host, float *x1, uint32_t *poolmax, void *stream)
 {
     DAGR_CHECK_ARG(g && p_host, "null argument");
+    DAGR_CHECK_ARG(p_host->pool_mean == 0, "mean pooling needs the per-voxel kernel (dagr_l1_conv_b_pool_voxel)");
     if (N <= 0) return DAGR_OK;
     size_t smem = l1_smem_bytes(g);
     DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -553,9 +554,11 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
     const int s2 = T.run_len[2] > 0 ? T.run_start[2] : 0x7fffffff;
     const int d0 = T.run_off[0] - T.run_start[0], d1 = T.run_off[1] - T.run_start[1], d2 = T.run_off[2] - T.run_start[2];
 
+    bool pool_mean = false;                                              // pool1 aggregation (pooling.py:74-77); block-uniform
+    if constexpr (!MODE_A) pool_mean = P.pool_mean != 0;
     float m[16];
 #pragma unroll
-    for (int c = 0; c < 16; c++) m[c] = -INFINITY;
+    for (int c = 0; c < 16; c++) m[c] = pool_mean ? 0.f : -INFINITY;
     long long sx = 0, sy = 0, st = 0;
     int tm = -2147483647;
     // Sparse voxels (at most one warp of nodes, e.g. the early windows of an inter-frame sequence): the per-thread chain of
@@ -755,7 +758,7 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
             float r = fmaf(o[c], P.scale[c], P.shift[c]) + skv[c];
             r = P.relu ? fmaxf(r, 0.f) : r;
             o[c] = r;
-            m[c] = fmaxf(m[c], r);
+            m[c] = pool_mean ? m[c] + r : fmaxf(m[c], r);
         }
         if (x1 != nullptr) {
             float4 *dst = reinterpret_cast<float4 *>(x1 + (int64_t)p * 16);
@@ -771,7 +774,10 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
 #pragma unroll
-        for (int c = 0; c < 16; c++) m[c] = fmaxf(m[c], __shfl_xor_sync(0xffffffffu, m[c], d));
+        for (int c = 0; c < 16; c++) {
+            const float o2 = __shfl_xor_sync(0xffffffffu, m[c], d);
+            m[c] = pool_mean ? m[c] + o2 : fmaxf(m[c], o2);
+        }
         sx += __shfl_xor_sync(0xffffffffu, sx, d);
         sy += __shfl_xor_sync(0xffffffffu, sy, d);
         st += __shfl_xor_sync(0xffffffffu, st, d);
@@ -786,7 +792,8 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
     const int nw = blockDim.x >> 5;
     if (threadIdx.x < 16) {
         float v = s_red[0][threadIdx.x];
-        for (int w2 = 1; w2 < nw; w2++) v = fmaxf(v, s_red[w2][threadIdx.x]);
+        for (int w2 = 1; w2 < nw; w2++) v = pool_mean ? v + s_red[w2][threadIdx.x] : fmaxf(v, s_red[w2][threadIdx.x]);
+        if (pool_mean) v = __fdiv_rn(v, (float)nown);                   // scatter_mean: sum / count
         if (persist != nullptr) {                                        // running per-voxel max of the stream
             if (min_idx > 0) v = fmaxf(v, persist[(int64_t)cell * 16 + threadIdx.x]);
             persist[(int64_t)cell * 16 + threadIdx.x] = v;
@@ -902,6 +909,7 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
     (void)tab;
     DAGR_CHECK_ARG(g && p_host, "null argument");
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
+    DAGR_CHECK_ARG(!(p_host->pool_mean && persist), "the running per-voxel aggregate of the event stream is a max (max_pool.py:59-62)");
     return cb2_launch<dagr_l1b_params_t, 2, false>(g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, p_host, skip_pre, min_idx,
                                                    persist, x1, cnt, pxy, tmean, tmax, xg, ldx, nullptr, nullptr, wl_hdr, wl_ids, defer,
                                                    (cudaStream_t)stream);

@@ -217,6 +217,7 @@ class Engine:
         s, b = _fold_bn(cb.norm); _fill(pb.scale, s); _fill(pb.shift, b)
         s, b = _fold_bn(cb.norm_skip); _fill(pb.sscale, s); _fill(pb.sshift, b)
         pb.relu = 1
+        pb.pool_mean = 0 if getattr(m.args, "pooling_aggr", "max") == "max" else 1            # net.py:79 (pool1 aggr)
         for i in range(3):
             pb.xs[i] = geom.slots_x[i]
         for j in range(5):
@@ -601,6 +602,9 @@ class Engine:
                       _lib.ptr(wl_hdr[4:]), _lib.ptr(self._zs(ws, "wl_conv_b", torch.int32)), defer[2], st)
             self._dense_report(ws, wl_hdr)
             if use_image:                                     # sampling_skip before pool1 (net.py:128-131)
+                if pk["l1b"].pool_mean:
+                    raise NotImplementedError("dagr_b200: pooling_aggr='mean' together with image fusion (the sampled image "
+                                              "channels are pooled by a per-voxel max kernel; every shipped config uses max)")
                 f1 = image_feats[1]
                 self._run("voxel_sample_max", lib.dagr_voxel_sample_max, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(f1),
                           int(f1.shape[1]), int(f1.shape[2]), int(f1.shape[3]), _lib.ptr(g1.x), c1, 16, st)

@@ -223,6 +223,7 @@ typedef struct {
     float scale[16], shift[16];   /* norm                                            */
     float sscale[16], sshift[16]; /* norm_skip                                       */
     int32_t relu;
+    int32_t pool_mean;            /* pool1 aggregation: 0 = max (every shipped config), 1 = mean (args.pooling_aggr) */
     /* slot u = 3*j + i is spline kernel xs[i] + 5*ys[j].  xs/ys/den describe the slot grid to tools; the kernels take
      * the basis weights from the host-built tables (geometry.py), never from in-kernel divisions (slower, measured) */
     int32_t xs[3], ys[5];

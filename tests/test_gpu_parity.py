@@ -822,3 +822,21 @@ def test_reloading_weights_after_graph_capture_takes_effect(use_image):
             assert_close(got, want_b, tol=1e-4, what="decoded after reload (image)")
         else:
             assert torch.equal(got, want_b), f"forward {k} after load_state_dict still uses old weights"
+
+
+@pytest.mark.parametrize("variant", ["k8_r4", "mean_pooling", "empty_middle_sample", "one_scale", "k1"])
+def test_config_variants_parity_vs_oracle(variant):
+    """corners of the config surface (config/*.yaml keys): fewer neighbours / smaller radius, mean pooling, a sample without
+    events inside the batch, a single head scale, self loops only."""
+    from dagr_b200.data import EventBatch
+    W, H, B = 320, 215, 3
+    over = dict(k8_r4=dict(max_neighbors=8, radius=0.006), mean_pooling=dict(pooling_aggr="mean"), empty_middle_sample={},
+                one_scale=dict(num_scales=1), k1=dict(max_neighbors=1))[variant]
+    model, args = make_model("n", H, W, batch_size=B, **over)
+    model.cuda()
+    raw, data = make_inputs(B, 7000, W, H, seed=13, kind="clustered", ragged=True)
+    if variant == "empty_middle_sample":
+        keep = data.batch != 1
+        data = EventBatch(x=data.x[keep], pos=data.pos[keep], batch=data.batch[keep], width=data.width, height=data.height,
+                          time_window=data.time_window, num_graphs=B)
+    _check_forward(model, args, data, B, H, W)
