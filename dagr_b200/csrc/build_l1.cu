@@ -585,15 +585,13 @@ extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *sta
     if (deferring) {
         const size_t smem = bl_smem_bytes(g, BL_CAP, BL_THREADS);
         auto kern = k_l1_build<BL_CAP, 4>;
-        DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        DAGR_CUDA(dagr_allow_smem(kern, smem, true));
         kern<<<cells, BL_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab, *p_host, do_conv, min_idx,
                                                                 flags, nbr, off, cellmask, xa, wl_hdr, wl_ids, 1);
     } else {
         const size_t smem = bl_smem_bytes(g, BL_CAP_LEAN, BL_THREADS);
         auto kern = k_l1_build<BL_CAP_LEAN, 5>;
-        DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        DAGR_CUDA(dagr_allow_smem(kern, smem, true));
         kern<<<cells, BL_THREADS, smem, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab, *p_host, do_conv, min_idx,
                                                                 flags, nbr, off, cellmask, xa, wl_hdr, wl_ids, 0);
     }
@@ -606,7 +604,7 @@ extern "C" int dagr_l1_build(const dagr_geom_t *g, int64_t N, const int32_t *sta
             DAGR_CUDA(cudaGetDevice(&dev));
             DAGR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         }
-        DAGR_CUDA(cudaFuncSetAttribute(k_l1_build_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+        DAGR_CUDA(dagr_allow_smem(k_l1_build_dense, smem_big));
         k_l1_build_dense<<<n_sm, BL_THREADS_BIG, smem_big, (cudaStream_t)stream>>>(*g, N, start, (const int2 *)ti, xyb, feat_s, tab,
                                                                                     *p_host, do_conv, min_idx, flags, nbr, off,
                                                                                     cellmask, xa, wl_hdr, wl_ids);

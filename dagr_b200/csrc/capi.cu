@@ -13,6 +13,30 @@ void dagr_set_error(const char *fmt, ...)
 }
 
 extern "C" const char *dagr_last_error(void) { return g_err; }
+
+// ---- raise-only opt-in shared memory (see common.cuh) ---------------------------------------------------------------
+#include <map>
+#include <mutex>
+#include <utility>
+cudaError_t dagr_allow_smem_impl(const void *kernel, size_t bytes, bool max_carveout)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> allowed;          // (device, kernel) -> bytes granted so far
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = allowed.find({dev, kernel});
+    if (it != allowed.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    if (max_carveout && it == allowed.end()) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
+    allowed[{dev, kernel}] = bytes;
+    return cudaSuccess;
+}
 extern "C" int dagr_abi_version(void) { return DAGR_ABI_VERSION; }
 
 #include <string.h>

@@ -376,7 +376,7 @@ static int launch_grid_conv_sk(const dagr_grid_t *gr, const int32_t *cnt, const 
     const size_t a_bytes = (size_t)SK_SLOTS * Cin * CPB * sizeof(float), p_bytes = (size_t)SK_WARPS * CPB * Cout * sizeof(float);
     const size_t smem = (Cout <= 64) ? (a_bytes > p_bytes ? a_bytes : p_bytes) : a_bytes + p_bytes;
     if (smem > 200 * 1024) return -1;
-    cudaError_t e = cudaFuncSetAttribute(k_grid_conv_sk<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = dagr_allow_smem(k_grid_conv_sk<CPB>, smem);
     if (e != cudaSuccess) return -2;
     k_grid_conv_sk<CPB><<<dagr_div_up(cells, CPB), SK_WARPS * 32, smem, st>>>(*gr, cnt, pxy, mask, xin, ldin, Cin, Cout, weight, rootT, bias,
                                                                             scale, shift, skip, relu, den_x, den_y, out);
@@ -405,7 +405,7 @@ extern "C" int dagr_grid_conv(const dagr_grid_t *gr, const int32_t *cnt, const i
         // very wide layers: v1 kernel (one warp per voxel)
         const size_t smem = (size_t)GC_WARPS * GC_SLOTS * Cin * sizeof(float);
         DAGR_CHECK_ARG(smem <= 200 * 1024, "Cin too large for the grid conv kernels");
-        DAGR_CUDA(cudaFuncSetAttribute(k_grid_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DAGR_CUDA(dagr_allow_smem(k_grid_conv, smem));
         k_grid_conv<<<dagr_div_up(cells, GC_WARPS), GC_WARPS * 32, smem, st>>>(
             *gr, cnt, pxy, mask, xin, ldin, Cin, Cout, weight, rootT, bias, scale, shift, skip, relu, den_x, den_y, out);
     }

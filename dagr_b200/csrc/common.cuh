@@ -24,6 +24,17 @@ void dagr_set_error(const char *fmt, ...);
          if (e__ != cudaSuccess) { dagr_set_error("%s: %s", __func__, cudaGetErrorString(e__)); \
                                    return DAGR_E_CUDA; } } while (0)
 
+// Opt-in dynamic shared memory of a kernel, RAISE-ONLY.  The attribute is process-global state of the function: a launcher that
+// sets it to "this launch's size" lowers it again for the next, smaller launch.  A captured kernel node keeps the value it was
+// captured with, but tools that re-launch the nodes of a graph one by one (ncu's default per-node graph profiling) use the
+// CURRENT value and a node that needs more fails to launch.  capi.cu keeps the per-function maximum (and saves the driver
+// call on every later launch).
+cudaError_t dagr_allow_smem_impl(const void *kernel, size_t bytes, bool max_carveout);
+template <class K> static inline cudaError_t dagr_allow_smem(K kernel, size_t bytes, bool max_carveout = false)
+{
+    return dagr_allow_smem_impl(reinterpret_cast<const void *>(kernel), bytes, max_carveout);
+}
+
 static inline int dagr_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // exclusive prefix sum of n ints (graph.cu); blocksums: int[dagr_scan_blocks(n) + 2]; the grand total is left in

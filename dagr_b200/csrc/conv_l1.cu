@@ -135,7 +135,7 @@ extern "C" int dagr_l1_conv_a(const dagr_geom_t *g, int64_t N, const uint32_t *x
     DAGR_CHECK_ARG(g && p_host, "null argument");
     if (N <= 0) return DAGR_OK;
     size_t smem = l1_smem_bytes(g);
-    DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAGR_CUDA(dagr_allow_smem(k_l1_conv_a, smem));
     k_l1_conv_a<<<dagr_div_up(N, L1_THREADS), L1_THREADS, smem, (cudaStream_t)stream>>>(
         *g, N, xyb, feat_s, nbr, off, tab, *p_host, xa);
     DAGR_CHECK_LAUNCH();
@@ -291,7 +291,7 @@ extern "C" int dagr_l1_conv_b_pool(const dagr_geom_t *g, int64_t N, const uint32
     DAGR_CHECK_ARG(p_host->pool_mean == 0, "mean pooling needs the per-voxel kernel (dagr_l1_conv_b_pool_voxel)");
     if (N <= 0) return DAGR_OK;
     size_t smem = l1_smem_bytes(g);
-    DAGR_CUDA(cudaFuncSetAttribute(k_l1_conv_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAGR_CUDA(dagr_allow_smem(k_l1_conv_b, smem));
     k_l1_conv_b<<<dagr_div_up(N, L1_THREADS), L1_THREADS, smem, (cudaStream_t)stream>>>(
         *g, N, xyb, feat_s, xa, nbr, off, tab, *p_host, x1, poolmax);
     DAGR_CHECK_LAUNCH();
@@ -876,8 +876,7 @@ static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, con
     const int cells = g->B * g->ny1 * g->nx1;
     const size_t smem = cb2_smem_bytes(g, CB2_CAP, CB2_THREADS);
     auto kern = k_l1_conv_b2<PT, NCH, MODE_A>;
-    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DAGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DAGR_CUDA(dagr_allow_smem(kern, smem, true));
     kern<<<cells, CB2_THREADS, smem, st>>>(*g, N, start, xyb, ti, feat_s, xa, nbr, off, *p_host, skip_pre, min_idx, persist, x1, cnt, pxy,
                                            tmean, tmax, xg, ldx, xa_out, skip_out, wl_hdr, wl_ids,
                                            (wl_hdr != nullptr && wl_ids != nullptr && defer) ? 1 : 0);
@@ -891,7 +890,7 @@ static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, con
         }
         const size_t smem_big = cb2_smem_bytes(g, CB2_CAP_BIG, CB2_THREADS_BIG);
         auto kd = k_l1_conv_b2_dense<PT, NCH, MODE_A>;
-        DAGR_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+        DAGR_CUDA(dagr_allow_smem(kd, smem_big));
         kd<<<n_sm, CB2_THREADS_BIG, smem_big, st>>>(*g, N, start, xyb, ti, feat_s, xa, nbr, off, *p_host, skip_pre, min_idx, persist, x1,
                                                     cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, wl_hdr, wl_ids);
         DAGR_CHECK_LAUNCH();
