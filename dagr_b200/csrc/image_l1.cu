@@ -120,6 +120,10 @@ __device__ __forceinline__ float vs_sample(const float *__restrict__ img, const 
     return acc;
 }
 
+// MEAN: the pooling's aggregation (pooling.py:74-77, args.pooling_aggr); max in every shipped config
+template <bool MEAN> __device__ __forceinline__ float vs_comb(float a, float b) { return MEAN ? a + b : fmaxf(a, b); }
+
+template <bool MEAN>
 __global__ void __launch_bounds__(VS_THREADS)
 k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
                    const float *__restrict__ img, int C, int h, int w, float *__restrict__ xg, int ldx, int c0)
@@ -158,7 +162,7 @@ k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const
         const int epw = 32 / lpe, sub = lane / lpe, cl = (lane % lpe) * 8;
         float m[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) m[k] = -INFINITY;
+        for (int k = 0; k < 8; k++) m[k] = MEAN ? 0.f : -INFINITY;
         for (int pb = p0 + wid * epw; pb < p1; pb += (VS_THREADS / 32) * epw) {
             const int p = pb + sub;
             if (p < p1) {
@@ -192,13 +196,13 @@ k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], acc[k]);
+                for (int k = 0; k < 8; k++) m[k] = vs_comb<MEAN>(m[k], acc[k]);
             }
         }
         // lanes with the same channel block sit lpe apart
         for (int d = lpe; d < 32; d <<= 1)
 #pragma unroll
-            for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], __shfl_xor_sync(0xffffffffu, m[k], d));
+            for (int k = 0; k < 8; k++) m[k] = vs_comb<MEAN>(m[k], __shfl_xor_sync(0xffffffffu, m[k], d));
         float *s_mm = &s_m[0][0];                                          // [warps][128]
         if (lane < lpe) {
 #pragma unroll
@@ -207,13 +211,14 @@ k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const
         __syncthreads();
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             float v = s_mm[c];
-            for (int w2 = 1; w2 < VS_THREADS / 32; w2++) v = fmaxf(v, s_mm[w2 * 128 + c]);
-            xg[(int64_t)cell * ldx + c0 + c] = v;
+            for (int w2 = 1; w2 < VS_THREADS / 32; w2++) v = vs_comb<MEAN>(v, s_mm[w2 * 128 + c]);
+            xg[(int64_t)cell * ldx + c0 + c] = MEAN ? __fdiv_rn(v, (float)(p1 - p0)) : v;
         }
         return;
     }
     for (int cb = 0; cb < C; cb += 128) {
-        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        const float ident = MEAN ? 0.f : -INFINITY;
+        float m[4] = {ident, ident, ident, ident};
         for (int p = p0 + wid; p < p1; p += VS_THREADS / 32) {
             const uint32_t wd = xyb[p];
             const int x = wd & 0xfff, y = (wd >> 12) & 0xfff;
@@ -222,8 +227,8 @@ k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const
             for (int k = 0; k < 4; k++) {
                 const int c = cb + lane + 32 * k;
                 if (c < C)
-                    m[k] = fmaxf(m[k], staged ? vs_sample<true>(img, s_patch, g.B, C, h, w, c, bl, zb, yb, xb, ph, pw)
-                                              : vs_sample<false>(img, s_patch, g.B, C, h, w, c, bl, zb, yb, xb, ph, pw));
+                    m[k] = vs_comb<MEAN>(m[k], staged ? vs_sample<true>(img, s_patch, g.B, C, h, w, c, bl, zb, yb, xb, ph, pw)
+                                                      : vs_sample<false>(img, s_patch, g.B, C, h, w, c, bl, zb, yb, xb, ph, pw));
             }
         }
 #pragma unroll
@@ -232,19 +237,20 @@ k_voxel_sample_max(const dagr_geom_t g, const int32_t *__restrict__ start, const
         const int c = cb + threadIdx.x;
         if (c < C) {
             float v = s_m[0][threadIdx.x];
-            for (int w2 = 1; w2 < VS_THREADS / 32; w2++) v = fmaxf(v, s_m[w2][threadIdx.x]);
-            xg[(int64_t)cell * ldx + c0 + c] = v;
+            for (int w2 = 1; w2 < VS_THREADS / 32; w2++) v = vs_comb<MEAN>(v, s_m[w2][threadIdx.x]);
+            xg[(int64_t)cell * ldx + c0 + c] = MEAN ? __fdiv_rn(v, (float)(p1 - p0)) : v;
         }
         __syncthreads();
     }
 }
 
 extern "C" int dagr_voxel_sample_max(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb, const float *img,
-                                     int C, int h, int w, float *xg, int ldx, int c0, void *stream)
+                                     int C, int h, int w, float *xg, int ldx, int c0, int pool_mean, void *stream)
 {
     (void)N;
     const int cells = g->B * g->ny1 * g->nx1;
-    k_voxel_sample_max<<<cells, VS_THREADS, 0, (cudaStream_t)stream>>>(*g, start, xyb, img, C, h, w, xg, ldx, c0);
+    if (pool_mean) k_voxel_sample_max<true><<<cells, VS_THREADS, 0, (cudaStream_t)stream>>>(*g, start, xyb, img, C, h, w, xg, ldx, c0);
+    else           k_voxel_sample_max<false><<<cells, VS_THREADS, 0, (cudaStream_t)stream>>>(*g, start, xyb, img, C, h, w, xg, ldx, c0);
     DAGR_CHECK_LAUNCH();
     return DAGR_OK;
 }

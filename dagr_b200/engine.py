@@ -602,12 +602,9 @@ class Engine:
                       _lib.ptr(wl_hdr[4:]), _lib.ptr(self._zs(ws, "wl_conv_b", torch.int32)), defer[2], st)
             self._dense_report(ws, wl_hdr)
             if use_image:                                     # sampling_skip before pool1 (net.py:128-131)
-                if pk["l1b"].pool_mean:
-                    raise NotImplementedError("dagr_b200: pooling_aggr='mean' together with image fusion (the sampled image "
-                                              "channels are pooled by a per-voxel max kernel; every shipped config uses max)")
                 f1 = image_feats[1]
                 self._run("voxel_sample_max", lib.dagr_voxel_sample_max, g, N, _lib.ptr(ws["start"]), _lib.ptr(ws["xyb"]), _lib.ptr(f1),
-                          int(f1.shape[1]), int(f1.shape[2]), int(f1.shape[3]), _lib.ptr(g1.x), c1, 16, st)
+                          int(f1.shape[1]), int(f1.shape[2]), int(f1.shape[3]), _lib.ptr(g1.x), c1, 16, int(pk["l1b"].pool_mean), st)
         else:
             self._run("l1_conv_b_pool", lib.dagr_l1_conv_b_pool, g, N, _lib.ptr(ws["xyb"]), _lib.ptr(ws["feat_s"]), _lib.ptr(ws["xa"]),
                       _lib.ptr(nbr), _lib.ptr(off), _lib.ptr(geom.d_tab1), C.byref(pk["l1b"]), _lib.ptr(x1), _lib.ptr(poolmax), st)

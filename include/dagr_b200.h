@@ -192,10 +192,11 @@ int dagr_l1_conv_a_image(const dagr_geom_t *g, int64_t N, const int32_t *start, 
                          int32_t *wl_hdr, int32_t *wl_ids, int defer /* dense-voxel work list, see dagr_l1_conv_b_pool_voxel */,
                          void *stream);
 
-/* per-voxel channel max of image features sampled at the voxel's events (sampling_skip before pool1,
- * net.py:128-131): xg[cell*ldx + c0 + c], c < C, empty voxels -> 0 */
+/* per-voxel channel max (pool_mean = 0, every shipped config) or mean (pool_mean = 1, args.pooling_aggr) of image features
+ * sampled at the voxel's events (sampling_skip before pool1, net.py:128-131): xg[cell*ldx + c0 + c], c < C, empty voxels -> 0 */
 int dagr_voxel_sample_max(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb,
-                          const float *img /*[B,C,h,w]*/, int C, int h, int w, float *xg, int ldx, int c0, void *stream);
+                          const float *img /*[B,C,h,w]*/, int C, int h, int w, float *xg, int ldx, int c0, int pool_mean,
+                          void *stream);
 
 int dagr_graph_export(const dagr_geom_t *g, int64_t N, const int32_t *perm, const int32_t *ti,
                       const int32_t *nbr, int32_t *inv, int32_t *rowptr, int32_t *blocksums,

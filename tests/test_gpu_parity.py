@@ -410,12 +410,13 @@ def test_last_event_at_t_equals_T_quirk_h3a():
     assert q["levels"][0]["x"].shape[0] == o["levels"][0]["x"].shape[0] + 1
 
 
-@pytest.mark.parametrize("W,H,B,n,size", [(240, 180, 2, 5000, "n"), (320, 215, 1, 9000, "s")])
-def test_image_fusion_parity_vs_oracle(W, H, B, n, size):
+@pytest.mark.parametrize("W,H,B,n,size,img_net", [(240, 180, 2, 5000, "n", "resnet18"), (320, 215, 1, 9000, "s", "resnet18"),
+                                                  (640, 480, 2, 40000, "s", "resnet50")])       # the last one: config 3's shape
+def test_image_fusion_parity_vs_oracle(W, H, B, n, size, img_net):
     """use_image: sampled ResNet features enter every Layer input and every pooling, CNN head maps are added to the
     dense outputs.  The dense trunk is torch/cuDNN on both sides (its tensors are handed to the oracle)."""
     from dagr_b200.data import format_data, synth_batch
-    model, args = make_model(size, H, W, use_image=True, img_net="resnet18", batch_size=B)
+    model, args = make_model(size, H, W, use_image=True, img_net=img_net, batch_size=B)
     model.cuda()
     raw = synth_batch(B, n, W, H, seed=77, kind="clustered", with_image=True, ragged=True)
     data = format_data(raw.clone())
@@ -840,3 +841,13 @@ def test_config_variants_parity_vs_oracle(variant):
         data = EventBatch(x=data.x[keep], pos=data.pos[keep], batch=data.batch[keep], width=data.width, height=data.height,
                           time_window=data.time_window, num_graphs=B)
     _check_forward(model, args, data, B, H, W)
+
+
+def test_mean_pooling_with_image_fusion_parity_vs_oracle():
+    """pooling_aggr: mean also averages the sampled image channels appended before pool1 (net.py:128-131, pooling.py:76-77)."""
+    from dagr_b200.data import format_data, synth_batch
+    W, H, B = 240, 180, 2
+    model, args = make_model("n", H, W, use_image=True, img_net="resnet18", batch_size=B, pooling_aggr="mean")
+    model.cuda()
+    raw = synth_batch(B, 5000, W, H, seed=78, kind="clustered", with_image=True, ragged=True)
+    _check_forward(model, args, format_data(raw.clone()), B, H, W, image=True, check_public=False)
