@@ -484,17 +484,24 @@ struct CB2Shared {
 // chunk-major for conv_block2, plus the layer's skip branch BN(Linear(x0)) -> skip_out; no pooling).
 // work list: wl_hdr[0] = number of voxels beyond this instance's staging capacity (queued in wl_ids when `defer`, otherwise
 // only counted and gathered from global memory / L2), wl_hdr[1] = pop cursor of the dense kernel
-template <class PT, int NCH, bool MODE_A, int CAP, int THREADS>
+template <class PT, int NCH, bool MODE_A, int CAP, int THREADS, bool POOL_MEAN, bool PLAIN>
 __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
              const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
              const int32_t *__restrict__ nbr, const uint16_t *__restrict__ off,
-             const PT &P, const float *__restrict__ skip_pre, const int min_idx,
-             float *__restrict__ persist, float *__restrict__ x1, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
+             const PT &P, const float *__restrict__ skip_pre_in, const int min_idx_in,
+             float *__restrict__ persist_in, float *__restrict__ x1_in, int32_t *__restrict__ cnt, int32_t *__restrict__ pxy,
              float *__restrict__ tmean, float *__restrict__ tmax, float *__restrict__ xg, int ldx,
              float *__restrict__ xa_out, float *__restrict__ skip_out,
              const int cell, unsigned char *smem_raw, CB2Shared<THREADS> &S, uint32_t &parity,
              int32_t *__restrict__ wl_hdr, int32_t *__restrict__ wl_ids, const int defer)
 {
+    // PLAIN = the synchronous events-only forward (no incremental mode, no running stream max, no per-node output, skip branch
+    // computed here, ReLU): with these known at compile time the max instance is 1.2 % faster (1.450 -> 1.433 ms, same-box A/B)
+    const int min_idx = PLAIN ? 0 : min_idx_in;
+    float *const persist = PLAIN ? nullptr : persist_in;
+    float *const x1 = PLAIN ? nullptr : x1_in;
+    const float *const skip_pre = PLAIN ? nullptr : skip_pre_in;
+    const bool relu = PLAIN ? true : (P.relu != 0);
     CB2Tile &T = S.T;
     uint64_t &s_bar = S.bar;
     auto &s_red = S.red;
@@ -554,8 +561,9 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
     const int s2 = T.run_len[2] > 0 ? T.run_start[2] : 0x7fffffff;
     const int d0 = T.run_off[0] - T.run_start[0], d1 = T.run_off[1] - T.run_start[1], d2 = T.run_off[2] - T.run_start[2];
 
-    bool pool_mean = false;                                              // pool1 aggregation (pooling.py:74-77); block-uniform
-    if constexpr (!MODE_A) pool_mean = P.pool_mean != 0;
+    // pool1 aggregation (pooling.py:74-77).  A template parameter: as a run-time flag (selects in the row epilogue and in the
+    // reductions, one more live predicate) it cost the max instance 2.6 % (1.455 -> 1.493 ms, same-box A/B)
+    constexpr bool pool_mean = POOL_MEAN && !MODE_A;
     float m[16];
 #pragma unroll
     for (int c = 0; c < 16; c++) m[c] = pool_mean ? 0.f : -INFINITY;
@@ -607,6 +615,8 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
                 __syncthreads();                                        // everyone is done with the previous half's rows
                 if (threadIdx.x == 0) {
                     // TMA: three contiguous runs of 32-byte half-rows, global -> shared, completion on the mbarrier
+                    // (issuing the first half during the CTA's set-up, so that it flies while the tables and ELL rows are
+                    // fetched, was measured: 1.495 -> 1.500 ms; the other three CTAs of the SM already hide that latency)
                     mbar_expect_tx(&s_bar, (uint32_t)total * 32u);
                     for (int rr = 0; rr < 3; rr++)
                         if (T.run_len[rr] > 0)
@@ -719,7 +729,7 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const float r = fmaf(o[c], P.scale[c], P.shift[c]);
-                o[c] = P.relu ? fmaxf(r, 0.f) : r;
+                o[c] = relu ? fmaxf(r, 0.f) : r;
                 sk[c] = fmaf(sk[c], P.sscale[c], P.sshift[c]);
             }
             float4 *dst = reinterpret_cast<float4 *>(xa_out + (int64_t)p * 8);
@@ -756,10 +766,11 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             float r = fmaf(o[c], P.scale[c], P.shift[c]) + skv[c];
-            r = P.relu ? fmaxf(r, 0.f) : r;
+            r = relu ? fmaxf(r, 0.f) : r;
             o[c] = r;
-            m[c] = pool_mean ? m[c] + r : fmaxf(m[c], r);
         }
+#pragma unroll
+        for (int c = 0; c < 16; c++) m[c] = pool_mean ? m[c] + o[c] : fmaxf(m[c], o[c]);
         if (x1 != nullptr) {
             float4 *dst = reinterpret_cast<float4 *>(x1 + (int64_t)p * 16);
             dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -814,7 +825,7 @@ __device__ __forceinline__ void cb2_voxel(const dagr_geom_t &g, int64_t N, const
 }
 
 
-template <class PT, int NCH, bool MODE_A>
+template <class PT, int NCH, bool MODE_A, bool POOL_MEAN, bool PLAIN>
 __global__ void __launch_bounds__(CB2_THREADS, MODE_A ? 3 : 4)
 k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
              const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
@@ -829,12 +840,12 @@ k_l1_conv_b2(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, 
     __shared__ __align__(8) CB2Shared<CB2_THREADS> S;
     if (threadIdx.x == 0) mbar_init(&S.bar, 1);                         // made visible by the routine's first __syncthreads
     uint32_t parity = 0;
-    cb2_voxel<PT, NCH, MODE_A, CB2_CAP, CB2_THREADS>(g, N, start, xyb, ti, feat_s, xa, nbr, off, P, skip_pre, min_idx, persist, x1, cnt, pxy,
+    cb2_voxel<PT, NCH, MODE_A, CB2_CAP, CB2_THREADS, POOL_MEAN, PLAIN>(g, N, start, xyb, ti, feat_s, xa, nbr, off, P, skip_pre, min_idx, persist, x1, cnt, pxy,
                                                       tmean, tmax, xg, ldx, xa_out, skip_out, (int)blockIdx.x, smem_raw, S, parity, wl_hdr, wl_ids, defer);
 }
 
 // dense voxels: persistent CTAs (one per SM) pop voxel ids from the work list the regular kernel filled
-template <class PT, int NCH, bool MODE_A>
+template <class PT, int NCH, bool MODE_A, bool POOL_MEAN, bool PLAIN>
 __global__ void __launch_bounds__(CB2_THREADS_BIG, 1)
 k_l1_conv_b2_dense(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ start, const uint32_t *__restrict__ xyb,
                    const int2 *__restrict__ ti, const float *__restrict__ feat_s, const float *__restrict__ xa,
@@ -856,7 +867,7 @@ k_l1_conv_b2_dense(const dagr_geom_t g, int64_t N, const int32_t *__restrict__ s
         __syncthreads();
         const int i = s_next;
         if (i >= count) break;
-        cb2_voxel<PT, NCH, MODE_A, CB2_CAP_BIG, CB2_THREADS_BIG>(g, N, start, xyb, ti, feat_s, xa, nbr, off, P, skip_pre, min_idx, persist, x1,
+        cb2_voxel<PT, NCH, MODE_A, CB2_CAP_BIG, CB2_THREADS_BIG, POOL_MEAN, PLAIN>(g, N, start, xyb, ti, feat_s, xa, nbr, off, P, skip_pre, min_idx, persist, x1,
                                                                   cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, wl_ids[i],
                                                                   smem_raw, S, parity, nullptr, nullptr, 0);
     }
@@ -867,7 +878,7 @@ static size_t cb2_smem_bytes(const dagr_geom_t *g, int cap, int threads)
     return (size_t)cap * 32 + 96 * 16 + (size_t)DAGR_ELL * threads * 4 + (size_t)g->ncell * 2 + 32;
 }
 
-template <class PT, int NCH, bool MODE_A>
+template <class PT, int NCH, bool MODE_A, bool POOL_MEAN = false, bool PLAIN = false>
 static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, const uint32_t *xyb, const int2 *ti, const float *feat_s,
                       const float *xa, const int32_t *nbr, const uint16_t *off, const PT *p_host, const float *skip_pre, int min_idx,
                       float *persist, float *x1, int32_t *cnt, int32_t *pxy, float *tmean, float *tmax, float *xg, int ldx,
@@ -875,7 +886,7 @@ static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, con
 {
     const int cells = g->B * g->ny1 * g->nx1;
     const size_t smem = cb2_smem_bytes(g, CB2_CAP, CB2_THREADS);
-    auto kern = k_l1_conv_b2<PT, NCH, MODE_A>;
+    auto kern = k_l1_conv_b2<PT, NCH, MODE_A, POOL_MEAN, PLAIN>;
     DAGR_CUDA(dagr_allow_smem(kern, smem, true));
     kern<<<cells, CB2_THREADS, smem, st>>>(*g, N, start, xyb, ti, feat_s, xa, nbr, off, *p_host, skip_pre, min_idx, persist, x1, cnt, pxy,
                                            tmean, tmax, xg, ldx, xa_out, skip_out, wl_hdr, wl_ids,
@@ -889,7 +900,7 @@ static int cb2_launch(const dagr_geom_t *g, int64_t N, const int32_t *start, con
             DAGR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         }
         const size_t smem_big = cb2_smem_bytes(g, CB2_CAP_BIG, CB2_THREADS_BIG);
-        auto kd = k_l1_conv_b2_dense<PT, NCH, MODE_A>;
+        auto kd = k_l1_conv_b2_dense<PT, NCH, MODE_A, POOL_MEAN, PLAIN>;
         DAGR_CUDA(dagr_allow_smem(kd, smem_big));
         kd<<<n_sm, CB2_THREADS_BIG, smem_big, st>>>(*g, N, start, xyb, ti, feat_s, xa, nbr, off, *p_host, skip_pre, min_idx, persist, x1,
                                                     cnt, pxy, tmean, tmax, xg, ldx, xa_out, skip_out, wl_hdr, wl_ids);
@@ -909,6 +920,14 @@ extern "C" int dagr_l1_conv_b_pool_voxel(const dagr_geom_t *g, int64_t N, const 
     DAGR_CHECK_ARG(g && p_host, "null argument");
     DAGR_CHECK_ARG(g->r <= 15, "radius must be <= 15 px (offsets are packed in 5 bits)");
     DAGR_CHECK_ARG(!(p_host->pool_mean && persist), "the running per-voxel aggregate of the event stream is a max (max_pool.py:59-62)");
+    if (p_host->pool_mean)
+        return cb2_launch<dagr_l1b_params_t, 2, false, true>(g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, p_host, skip_pre, min_idx,
+                                                             persist, x1, cnt, pxy, tmean, tmax, xg, ldx, nullptr, nullptr, wl_hdr, wl_ids,
+                                                             defer, (cudaStream_t)stream);
+    if (min_idx <= 0 && persist == nullptr && x1 == nullptr && skip_pre == nullptr && p_host->relu)
+        return cb2_launch<dagr_l1b_params_t, 2, false, false, true>(g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, p_host, nullptr, 0,
+                                                                    nullptr, nullptr, cnt, pxy, tmean, tmax, xg, ldx, nullptr, nullptr, wl_hdr,
+                                                                    wl_ids, defer, (cudaStream_t)stream);
     return cb2_launch<dagr_l1b_params_t, 2, false>(g, N, start, xyb, (const int2 *)ti, feat_s, xa, nbr, off, p_host, skip_pre, min_idx,
                                                    persist, x1, cnt, pxy, tmean, tmax, xg, ldx, nullptr, nullptr, wl_hdr, wl_ids, defer,
                                                    (cudaStream_t)stream);

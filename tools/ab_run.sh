@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 for v in "$@"; do
   lib=dagr_b200/build/variants/$v.so
   [ "$v" = "main" ] && lib=dagr_b200/libdagr_b200.so
-  DAGR_B200_LIB=$lib timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  DAGR_B200_LIB=$lib timeout 200 python bench.py --headline-only --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - "$v" <<'PY'
 import json, sys
 v = sys.argv[1]
