@@ -400,6 +400,9 @@ __device__ __forceinline__ void cb2_pass(int64_t N, int p, int n, const float *_
 #define CB2_UNROLL 1                                                    // measured: 1 -> 1.49 ms, 2 -> 1.56, 3 -> 1.58, 4 -> 1.68 (registers, I-cache)
 #endif
         constexpr int kUnroll = CB2_UNROLL;
+        // (40 % of this kernel's stall samples are short-scoreboard waits on this loop's shared-memory loads -- ELL word -> row
+        // address -> row is a chain of two dependent loads per edge.  Software prefetching was measured in a same-box A/B:
+        // next edge's ELL word one iteration ahead 1.435 -> 1.451 ms, next edge's row and table entries as well -> 1.576 ms.)
 #pragma unroll kUnroll
         for (int q = 0; q <= n; q++) {
             const uint32_t ell = s_ell[q * THREADS + tix];
