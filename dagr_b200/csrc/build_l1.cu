@@ -101,6 +101,21 @@ __device__ __forceinline__ void bl_probe(const dagr_geom_t &g, int64_t N, int p,
     n_out = active ? n : 0;
 }
 
+
+#ifndef BL_SHARED_ADDR
+#define BL_SHARED_ADDR 1
+#endif
+// explicit 32-bit shared-memory accesses for the ring walk: with generic pointers ptxas re-materialises the shared window base
+// (S2R SR_CgaCtaId + MOV + LEA) inside the pop loop instead of keeping it in a register: 1.457 -> 1.419 ms (same-box A/B).
+// The same treatment of phase B's seven table bases (the conv_a accumulation loop) costs registers the 45 accumulators do not
+// leave: stack 16 -> 40 bytes, 1.418 -> 1.555 ms -- that loop keeps its generic pointers.
+__device__ __forceinline__ uint32_t bl_sa(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t bl_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t bl_lds16(uint32_t a) { uint32_t v; asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ int bl_lds16s(uint32_t a) { int v; asm volatile("{ .reg .s16 t; ld.shared.s16 t, [%1]; cvt.s32.s16 %0, t; }" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ int2 bl_lds64(uint32_t a) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void bl_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
 // Ring walk with occupancy bitmasks.  For every time bucket e the CTA keeps, per tile row, a 32-bit mask of the
 // pixels whose bucket range is non-empty (and the transposed per-column masks).  Ring d of the spiral consists of
 // four straight segments (spiral.h: right column upwards, top row leftwards, left column downwards, bottom row
@@ -117,14 +132,19 @@ __device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, 
     const int kmax = g.K - 1;
     int n = active ? 0 : kmax;
     const uint32_t *occr = s_occ_r + eb * TH, *occc = s_occ_c + eb * TW;
+    constexpr bool SA = STAGED && BL_SHARED_ADDR;
+    const uint32_t a_rng = bl_sa(s_rng) + 2u * (uint32_t)eb, a_pbin = bl_sa(s_pbin), a_ti = bl_sa(s_ti), a_sp2 = bl_sa(s_sp2);
+    const uint32_t a_acc = bl_sa(s_acc) + 4u * threadIdx.x;
+    const int dt_us = g.dt_us;
     auto visit = [&](int pix, int c) {
-        const uint32_t rg = s_rng[pix * BL_NB + eb];
+        const uint32_t rg = SA ? bl_lds16(a_rng + (uint32_t)pix * (2u * BL_NB)) : (uint32_t)s_rng[pix * BL_NB + eb];
         const int lo = rg & 0xff, hi = rg >> 8;
-        const int base = (int)(s_pbin[pix] >> 8);
+        const int base = (int)((SA ? bl_lds32(a_pbin + 4u * (uint32_t)pix) : s_pbin[pix]) >> 8);
         for (int j = base + hi - 1; j >= base + lo && n < kmax; j--) {     // FIFO order: newest first
-            const int2 o = STAGED ? s_ti[j] : __ldg(ti + j);
-            if (o.y < me.y && me.x - o.x <= g.dt_us) {                      // ev_graph.cu:64-69
-                if (STAGED) s_acc[n * THREADS + threadIdx.x] = ((uint32_t)j << 10) | (uint32_t)c;
+            const int2 o = SA ? bl_lds64(a_ti + 8u * (uint32_t)j) : (STAGED ? s_ti[j] : __ldg(ti + j));
+            if (o.y < me.y && me.x - o.x <= dt_us) {                        // ev_graph.cu:64-69
+                if (SA) bl_sts32(a_acc + (uint32_t)n * (4u * THREADS), ((uint32_t)j << 10) | (uint32_t)c);
+                else if (STAGED) s_acc[n * THREADS + threadIdx.x] = ((uint32_t)j << 10) | (uint32_t)c;
                 else { nbr[(int64_t)n * N + p] = j; off[(int64_t)n * N + p] = (uint16_t)c; }
                 n++;
             }
@@ -156,7 +176,7 @@ __device__ __forceinline__ void bl_probe_rings(const dagr_geom_t &g, int64_t N, 
             int i;
             if (lo) { i = __ffs((int)lo) - 1; lo &= lo - 1; }
             else    { i = 32 + __ffs((int)hi) - 1; hi &= hi - 1; }
-            visit(tidx0 + s_sp2[cbase + i], cbase + i);
+            visit(tidx0 + (SA ? bl_lds16s(a_sp2 + 2u * (uint32_t)(cbase + i)) : (int)s_sp2[cbase + i]), cbase + i);
             if (n >= kmax) { lo = 0; hi = 0; }
         }
     }
