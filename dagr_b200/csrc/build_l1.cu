@@ -114,6 +114,24 @@ __device__ __forceinline__ uint32_t bl_lds32(uint32_t a) { uint32_t v; asm volat
 __device__ __forceinline__ uint32_t bl_lds16(uint32_t a) { uint32_t v; asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ int bl_lds16s(uint32_t a) { int v; asm volatile("{ .reg .s16 t; ld.shared.s16 t, [%1]; cvt.s32.s16 %0, t; }" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ int2 bl_lds64(uint32_t a) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+#ifndef BL_FAST_TABLES
+#define BL_FAST_TABLES 1            // exact reciprocal division + 32-bit shared addressing in the occupancy scan: 1.420 -> 1.411 ms (A/B)
+#endif
+// t / d for 0 <= t < 2^24 through a float reciprocal and one exact fix-up step (the generic 32-bit division is ~20 instructions);
+// anything else takes the plain division, so the result is always the C quotient
+__device__ __forceinline__ int bl_div(int t, int d, float inv)
+{
+#if BL_FAST_TABLES
+    if ((unsigned)t >= (1u << 24)) return t / d;
+    int q = (int)((float)t * inv);
+    const int r = t - q * d;
+    if (r < 0) q--; else if (r >= d) q++;
+    return q;
+#else
+    (void)inv;
+    return t / d;
+#endif
+}
 __device__ __forceinline__ void bl_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
 // Ring walk with occupancy bitmasks.  For every time bucket e the CTA keeps, per tile row, a 32-bit mask of the
@@ -259,6 +277,7 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
     unsigned char *s_rowv = s_colv + TWmax;                             // [THmax]
 
     const int dtw = max(g.dt_us, 1);
+    const float dtw_inv = 1.0f / (float)dtw;
     if (threadIdx.x == 0) {
         const int X0 = g.vx0[cx], X1 = g.vx0[cx + 1], Y0 = g.vy0[cy], Y1 = g.vy0[cy + 1];
         T.X0 = X0 - g.r; T.Y0 = Y0 - g.r; T.TW = X1 - X0 + 2 * g.r; T.TH = Y1 - Y0 + 2 * g.r;
@@ -340,7 +359,7 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
         for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
             const int2 r = ti[p];
             if (r.y < min_idx) continue;                                // incremental mode: only new events are processed
-            const int sl = r.x / dtw; mn = min(mn, sl); mx = max(mx, sl); mi = max(mi, r.y);
+            const int sl = bl_div(r.x, dtw, dtw_inv); mn = min(mn, sl); mx = max(mx, sl); mi = max(mi, r.y);
         }
         mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx); mi = __reduce_max_sync(0xffffffffu, mi);
         if ((threadIdx.x & 31) == 0) { atomicMin(&T.smin, mn); atomicMax(&T.smax, mx); atomicMax(&T.maxidx, mi); }
@@ -362,7 +381,7 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
             if (bucketed) {
                 int prev = 0;
                 for (int k = 0; k < vis; k++) {
-                    int bk = s_ti[base + k].x / dtw - sbase;
+                    int bk = bl_div(s_ti[base + k].x, dtw, dtw_inv) - sbase;
                     bk = min(max(bk, 0), BL_NB - 1);
                     if (bk < prev) T.unsorted = 1;                      // benign race: any writer sets 1
                     prev = bk;
@@ -391,6 +410,23 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
             // pixels -- no atomics (one atomicOr per pixel and bucket serialised on the row word: 6x the ideal wavefronts)
             for (int idx = threadIdx.x; idx < BL_NB * (TH + TW); idx += blockDim.x) {
                 uint32_t m = 0;
+#if BL_FAST_TABLES
+                if (idx < BL_NB * TH) {
+                    const int e = idx / TH, row = idx % TH;
+                    uint32_t a = bl_sa(s_rng) + 2u * (uint32_t)(row * TW * BL_NB + e);
+                    for (int x = 0; x < TW; x++, a += 2u * BL_NB) {
+                        const uint32_t rg = bl_lds16(a);
+                        m |= ((rg >> 8) > (rg & 0xff)) ? (1u << x) : 0u;
+                    }
+                } else {
+                    const int i2 = idx - BL_NB * TH, e = i2 / TW, col = i2 % TW;
+                    uint32_t a = bl_sa(s_rng) + 2u * (uint32_t)(col * BL_NB + e);
+                    for (int y = 0; y < TH; y++, a += 2u * BL_NB * (uint32_t)TW) {
+                        const uint32_t rg = bl_lds16(a);
+                        m |= ((rg >> 8) > (rg & 0xff)) ? (1u << y) : 0u;
+                    }
+                }
+#else
                 if (idx < BL_NB * TH) {
                     const int e = idx / TH, row = idx % TH;
                     for (int x = 0; x < TW; x++) {
@@ -404,6 +440,7 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
                         m |= ((rg >> 8) > (rg & 0xff)) ? (1u << y) : 0u;
                     }
                 }
+#endif
                 s_occ_r[idx] = m;                                        // s_occ_c follows s_occ_r: [BL_NB][TH] then [BL_NB][TW]
             }
         }
@@ -447,7 +484,7 @@ __device__ __forceinline__ void bl_voxel(const dagr_geom_t &g, int64_t N, const 
         }
         const int tx0 = active ? x - T.X0 : g.r, ty0 = active ? y - T.Y0 : g.r;
         int eb = 0;
-        if (bucketed) eb = min(max(me.x / dtw - sbase, 0), BL_NB - 1);
+        if (bucketed) eb = min(max(bl_div(me.x, dtw, dtw_inv) - sbase, 0), BL_NB - 1);
         int n;
         const int tidx0 = ty0 * TW + tx0;
         if (use_rings) {
